@@ -1,0 +1,162 @@
+"""B200-native `DiffRender`: same Scene contract as the reference module of this name, with the ray
+path (reference DiffRender.py:386-392, 420-438, 492-546 and optix_extend.cpp) replaced by
+libdrt_b200's fused CUDA kernels.  `import drt_b200.DiffRender as Render` is the drop-in for
+`import DiffRender as Render` (optim.py:6): module globals intIOR / resy / resx / device / Float are
+assignable after import (optim.py:178-182) and read at call time.
+
+No PyTorch op graph on the ray path: Scene.render_transparent is ONE autograd.Function whose
+forward is one kernel launch and whose backward is one kernel launch.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, trimesh_lite
+from . import optix  # the plugin module the reference JIT-builds (DiffRender.py:5-6)
+
+debug = False
+# render resolution (DiffRender.py:16-17)
+resy = 960
+resx = 1280
+Float = torch.float64
+device = "cuda"
+extIOR, intIOR = 1.00029, 1.5  # DiffRender.py:21
+
+_ptr = optix._ptr
+
+
+class Ray:
+    """SoA ray set + original pixel index (reference DiffRender.py:269-283)."""
+
+    def __init__(self, origin, direction, ray_ind=None):
+        self.origin = origin
+        self.direction = direction
+        self.ray_ind = torch.arange(len(origin), device=origin.device) if ray_ind is None else ray_ind
+
+    def select(self, mask):
+        return Ray(self.origin[mask], self.direction[mask], self.ray_ind[mask])
+
+    def __len__(self):
+        return len(self.ray_ind)
+
+
+class RefractTrace(torch.autograd.Function):
+    """(vertices, origin, ray_dir) -> (out_ori, out_dir, mask); d/d vertices only.
+
+    forward  = drt_trace_fwd : Q1 -> refract -> Q2 -> refract -> Q3, one launch
+    backward = drt_trace_bwd : replay of the cached hit records + analytic Jacobian + scatter-add
+    """
+
+    @staticmethod
+    def forward(ctx, vertices, origin, ray_dir, mesh, int_ior, ext_ior):
+        dev = mesh.device
+        V = vertices.detach()
+        if V.dtype != torch.float64 or origin.dtype != torch.float64 or ray_dir.dtype != torch.float64:
+            raise TypeError("render_transparent works in float64 like the reference (DiffRender.py:19)")
+        V = V.contiguous()
+        o = origin.detach().contiguous()
+        d = ray_dir.detach().contiguous()
+        if o.dim() != 2 or o.shape[1] != 3 or o.shape != d.shape:
+            raise ValueError(f"origin/ray_dir must both be [N,3], got {tuple(o.shape)} and {tuple(d.shape)}")
+        if V.shape[0] != mesh.n_verts:
+            raise ValueError(f"vertices has {V.shape[0]} rows, the mesh was built with {mesh.n_verts}")
+        n = o.shape[0]
+        out_ori = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        out_dir = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        mask = torch.empty((n, 3), dtype=torch.bool, device=dev)
+        rec = torch.empty((2, n), dtype=torch.int32, device=dev)
+        st = optix._stream_ptr(dev)
+        _lib.call("drt_trace_fwd", mesh._h, _ptr(V), _ptr(o), _ptr(d), n, float(ext_ior), float(int_ior), _ptr(out_ori),
+                  _ptr(out_dir), _ptr(mask), _ptr(rec[0]), _ptr(rec[1]), C.c_void_p(0), st)
+        ctx.mesh = mesh
+        ctx.iors = (float(ext_ior), float(int_ior))
+        ctx.save_for_backward(V, o, d, rec)
+        ctx.mark_non_differentiable(mask)
+        ctx.set_materialize_grads(False)
+        return out_ori, out_dir, mask
+
+    @staticmethod
+    def backward(ctx, g_ori, g_dir, _g_mask):
+        V, o, d, rec = ctx.saved_tensors
+        grad_V = torch.zeros_like(V)
+        if g_ori is None and g_dir is None:
+            return grad_V, None, None, None, None, None
+        n = o.shape[0]
+        if g_dir is None:
+            g_dir = torch.zeros_like(o)
+        g_dir = g_dir.contiguous()
+        g_ori = None if g_ori is None else g_ori.contiguous()
+        mesh = ctx.mesh
+        _lib.call("drt_trace_bwd", mesh._h, _ptr(V), _ptr(o), _ptr(d), n, ctx.iors[0], ctx.iors[1], _ptr(rec[0]),
+                  _ptr(rec[1]), _ptr(g_ori), _ptr(g_dir), _ptr(grad_V), optix._stream_ptr(mesh.device))
+        return grad_V, None, None, None, None, None
+
+
+class Scene:
+    """Same public surface as the reference Scene (DiffRender.py:298-546) for the methods optim.py
+    drives: ctor, update_mesh, update_verticex, render_transparent, render_mask, optix_intersect,
+    silhouette_edge, primary_visibility, dihedral_angle; attributes vertices, faces, mesh, mean_len."""
+
+    def __init__(self, mesh_path=None, cuda_device=0, vertices=None, faces=None):
+        self.cuda_device = cuda_device
+        self.optix_mesh = optix.optix_mesh(cuda_device)
+        self.refit = False  # True: update_verticex refits the BVH instead of rebuilding it
+        if mesh_path is not None:
+            self.update_mesh(mesh_path)
+        elif vertices is not None:
+            self.set_mesh(vertices, faces)
+
+    @property
+    def _dev(self):
+        return self.optix_mesh.device
+
+    # DiffRender.py:303-317
+    def update_mesh(self, mesh_path):
+        mesh = trimesh_lite.load(mesh_path, process=False)
+        assert mesh.is_watertight
+        self.set_mesh(mesh.vertices, mesh.faces, mesh)
+
+    def set_mesh(self, vertices, faces, mesh=None):
+        self.mesh = mesh if mesh is not None else trimesh_lite.TriMesh(
+            vertices.detach().cpu().numpy() if isinstance(vertices, torch.Tensor) else vertices,
+            faces.detach().cpu().numpy() if isinstance(faces, torch.Tensor) else faces)
+        self.vertices = torch.as_tensor(np.asarray(self.mesh.vertices), dtype=Float).to(self._dev)
+        self.faces = torch.as_tensor(np.asarray(self.mesh.faces), dtype=torch.long).to(self._dev)
+        # the float32 cast of DiffRender.py:311 happens inside the library (drt_bvh_build_f64)
+        self.optix_mesh.update_mesh(self.faces.to(torch.int32), self.vertices.detach())
+        self._edges_ready = False
+
+    # DiffRender.py:378-384 (without the per-iteration D2H copy and the dead init_VN)
+    def update_verticex(self, vertices):
+        self.optix_mesh.update_vert(vertices.detach(), refit=self.refit)
+        self.vertices = vertices
+        self._mesh_dirty = True
+
+    @property
+    def triangles(self):
+        return self.vertices[self.faces]
+
+    def sync_mesh(self):
+        """Bring self.mesh.vertices up to date (the reference does this D2H copy every iteration,
+        DiffRender.py:381; here only when the mesh is exported)."""
+        if getattr(self, "_mesh_dirty", False):
+            self.mesh.vertices = self.vertices.detach().cpu().numpy()
+            self._mesh_dirty = False
+        return self.mesh
+
+    # DiffRender.py:386-392
+    def optix_intersect(self, ray):
+        o = ray.origin.detach().to(torch.float32)
+        d = ray.direction.detach().to(torch.float32)
+        T, faces_ind = self.optix_mesh.intersect(torch.cat([o, d], dim=1))
+        return faces_ind.to(torch.long), T > 0
+
+    # DiffRender.py:420-432
+    def render_transparent(self, origin, ray_dir):
+        return RefractTrace.apply(self.vertices, origin, ray_dir, self.optix_mesh, intIOR, extIOR)
+
+    # DiffRender.py:434-438
+    def render_mask(self, origin, ray_dir):
+        _, hitted = self.optix_intersect(Ray(origin, ray_dir))
+        return hitted.to(Float)

@@ -1,0 +1,349 @@
+// capi.cu -- extern "C" boundary of libdrt_b200.so (see include/drt_b200.h).
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/drt_b200.h"
+#include "trace.cuh"
+
+using namespace drt;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(DRT_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+int ensure(T*& p, size_t& cap, size_t need)
+{
+    if (need <= cap) return DRT_OK;
+    if (p) CU(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    size_t n = need + need / 4 + 64;
+    CU(cudaMalloc(&p, n * sizeof(T)));
+    cap = n;
+    return DRT_OK;
+}
+
+inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+}  // namespace
+
+struct drt_bvh {
+    int device = 0;
+    int sm_count = 148;
+    int nF = 0, nV = 0;
+    bool built = false;
+    int64_t builds = 0, refits = 0;
+    // geometry copies
+    int32_t* F = nullptr;   size_t capF = 0;     // [nF*3]
+    float* V32 = nullptr;   size_t capV = 0;     // [nV*3]
+    // build scratch
+    uint64_t* keys = nullptr;  size_t capK = 0;  // 2*nF (double buffer)
+    uint32_t* vals = nullptr;  size_t capVa = 0; // 2*nF
+    void* cub_tmp = nullptr;   size_t cub_bytes = 0;
+    int2* children = nullptr;  size_t capCh = 0; // nF-1
+    int* parent = nullptr;     size_t capP = 0;  // 2nF-1
+    float4* blo = nullptr;     size_t capBl = 0; // 2nF-1
+    float4* bhi = nullptr;     size_t capBh = 0;
+    int* flags = nullptr;      size_t capFl = 0; // nF-1
+    unsigned* scene = nullptr;                   // 6 encoded floats + 1 int (bad index count) + pad
+    uint32_t* sorted_vals = nullptr;             // points into vals (which half holds the sorted ids)
+    // traversal data
+    float4* nodes = nullptr;   size_t capN = 0;
+    float4* tris = nullptr;    size_t capT = 0;
+
+    BvhView view() const { return BvhView{nodes, tris, F, nF}; }
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        int cur;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+// clamp + count out-of-range indices so that no later kernel can fault on a bad face list
+__global__ void copy_faces_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n3, int nV, int* __restrict__ bad)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n3) return;
+    int v = in[i];
+    if (v < 0 || v >= nV) { atomicAdd(bad, 1); v = min(max(v, 0), nV - 1); }
+    out[i] = v;
+}
+
+__global__ void init_scene_kernel(unsigned* scene, bool reset_bad)
+{
+    if (threadIdx.x < 3) scene[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) scene[threadIdx.x] = 0u;
+    else if (threadIdx.x == 6 && reset_bad) scene[6] = 0u;
+}
+
+int fit_and_emit(drt_bvh* b, cudaStream_t st)
+{
+    const int n = b->nF;
+    if (n <= 0) return DRT_OK;
+    if (n > 1) CU(cudaMemsetAsync(b->flags, 0, sizeof(int) * (size_t)(n - 1), st));
+    fit_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_vals, n, b->children, b->parent, b->blo, b->bhi,
+                                                    b->flags);
+    emit_nodes_kernel<<<blocks_for(n > 1 ? n - 1 : 1, 256), 256, 0, st>>>(n, b->children, b->blo, b->bhi, b->nodes);
+    emit_tris_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_vals, n, b->tris);
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int build_tree(drt_bvh* b, cudaStream_t st)
+{
+    const int n = b->nF;
+    b->built = true;
+    b->builds++;
+    if (n <= 0) return DRT_OK;
+    int rc;
+    if ((rc = ensure(b->keys, b->capK, 2 * (size_t)n))) return rc;
+    if ((rc = ensure(b->vals, b->capVa, 2 * (size_t)n))) return rc;
+    if ((rc = ensure(b->children, b->capCh, (size_t)n))) return rc;
+    if ((rc = ensure(b->parent, b->capP, 2 * (size_t)n))) return rc;
+    if ((rc = ensure(b->blo, b->capBl, 2 * (size_t)n))) return rc;
+    if ((rc = ensure(b->bhi, b->capBh, 2 * (size_t)n))) return rc;
+    if ((rc = ensure(b->flags, b->capFl, (size_t)n))) return rc;
+    if ((rc = ensure(b->nodes, b->capN, (size_t)kNodeQuads * (size_t)(n > 1 ? n - 1 : 1)))) return rc;
+    if ((rc = ensure(b->tris, b->capT, (size_t)kTriQuads * (size_t)n))) return rc;
+
+    init_scene_kernel<<<1, 32, 0, st>>>(b->scene, false);
+    centroid_bounds_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene);
+    morton_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene, b->keys, b->vals);
+    // (code, id) pairs: LSD radix sort over the 63 live key bits
+    cub::DoubleBuffer<uint64_t> dk(b->keys, b->keys + n);
+    cub::DoubleBuffer<uint32_t> dv(b->vals, b->vals + n);
+    size_t need = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, 63, st));
+    if (need > b->cub_bytes) {
+        if (b->cub_tmp) CU(cudaFree(b->cub_tmp));
+        b->cub_tmp = nullptr;
+        b->cub_bytes = 0;
+        CU(cudaMalloc(&b->cub_tmp, need + need / 4));
+        b->cub_bytes = need + need / 4;
+    }
+    size_t tmp_bytes = b->cub_bytes;
+    CU(cub::DeviceRadixSort::SortPairs(b->cub_tmp, tmp_bytes, dk, dv, n, 0, 63, st));
+    b->sorted_vals = dv.Current();
+    if (n > 1)
+        topology_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>(dk.Current(), n, b->children, b->parent);
+    CU(cudaGetLastError());
+    return fit_and_emit(b, st);
+}
+
+int set_vertices(drt_bvh* b, const float* V32, const double* V64, int nV, cudaStream_t st)
+{
+    int rc;
+    if ((rc = ensure(b->V32, b->capV, 3 * (size_t)(nV > 0 ? nV : 1)))) return rc;
+    b->nV = nV;
+    if (nV <= 0) return DRT_OK;
+    if (V32) CU(cudaMemcpyAsync(b->V32, V32, sizeof(float) * 3 * (size_t)nV, cudaMemcpyDeviceToDevice, st));
+    else cast_vertices_kernel<<<blocks_for(3 * (int64_t)nV, 256), 256, 0, st>>>(V64, b->V32, 3 * nV);
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int build_common(drt_bvh* b, const int32_t* F, int nF, const float* V32, const double* V64, int nV, void* stream)
+{
+    if (!b) return fail(DRT_ERR_INVALID, "drt_bvh_build: null handle");
+    if (nF < 0 || nV < 0) return fail(DRT_ERR_INVALID, "drt_bvh_build: negative size (nF=%d, nV=%d)", nF, nV);
+    if ((nF > 0 && !F) || (nV > 0 && !V32 && !V64)) return fail(DRT_ERR_INVALID, "drt_bvh_build: null F or V");
+    if (nF > 0 && nV == 0) return fail(DRT_ERR_INVALID, "drt_bvh_build: faces without vertices");
+    DeviceGuard g(b->device);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", b->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = set_vertices(b, V32, V64, nV, st))) return rc;
+    if ((rc = ensure(b->F, b->capF, 3 * (size_t)(nF > 0 ? nF : 1)))) return rc;
+    b->nF = nF;
+    init_scene_kernel<<<1, 32, 0, st>>>(b->scene, true);
+    if (nF > 0) copy_faces_kernel<<<blocks_for(3 * (int64_t)nF, 256), 256, 0, st>>>(F, b->F, 3 * nF, nV, (int*)(b->scene + 6));
+    CU(cudaGetLastError());
+    return build_tree(b, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int drt_version(void) { return 1000; }
+
+const char* drt_last_error(void) { return g_err; }
+
+int drt_bvh_create(int device, drt_bvh** out)
+{
+    if (!out) return fail(DRT_ERR_INVALID, "drt_bvh_create: out is null");
+    *out = nullptr;
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(DRT_ERR_INVALID, "drt_bvh_create: device %d out of range (%d visible)", device, count);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    drt_bvh* b = new drt_bvh();
+    b->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    b->sm_count = prop.multiProcessorCount;
+    CU(cudaMalloc(&b->scene, 8 * sizeof(unsigned)));
+    CU(cudaMemset(b->scene, 0, 8 * sizeof(unsigned)));
+    *out = b;
+    return DRT_OK;
+}
+
+int drt_bvh_destroy(drt_bvh* b)
+{
+    if (!b) return DRT_OK;
+    DeviceGuard g(b->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {b->F, b->V32, b->keys, b->vals, b->cub_tmp, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete b;
+    return DRT_OK;
+}
+
+int drt_bvh_build(drt_bvh* b, const int32_t* F, int32_t nF, const float* V32, int32_t nV, void* stream)
+{
+    if (nV > 0 && !V32) return fail(DRT_ERR_INVALID, "drt_bvh_build: V32 is null");
+    return build_common(b, F, nF, V32, nullptr, nV, stream);
+}
+
+int drt_bvh_build_f64(drt_bvh* b, const int32_t* F, int32_t nF, const double* V64, int32_t nV, void* stream)
+{
+    if (nV > 0 && !V64) return fail(DRT_ERR_INVALID, "drt_bvh_build_f64: V64 is null");
+    return build_common(b, F, nF, nullptr, V64, nV, stream);
+}
+
+int drt_bvh_update_vert(drt_bvh* b, const float* V32, const double* V64, int32_t nV, int refit, void* stream)
+{
+    if (!b) return fail(DRT_ERR_INVALID, "drt_bvh_update_vert: null handle");
+    if (!b->built) return fail(DRT_ERR_STATE, "drt_bvh_update_vert: update_mesh has not been called (no faces)");
+    if ((V32 == nullptr) == (V64 == nullptr)) return fail(DRT_ERR_INVALID, "drt_bvh_update_vert: exactly one of V32/V64 must be given");
+    if (nV != b->nV) return fail(DRT_ERR_INVALID, "drt_bvh_update_vert: vertex count %d != %d of the current faces", nV, b->nV);
+    DeviceGuard g(b->device);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", b->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = set_vertices(b, V32, V64, nV, st))) return rc;
+    if (refit) { b->refits++; return fit_and_emit(b, st); }
+    return build_tree(b, st);
+}
+
+int drt_bvh_info(const drt_bvh* b, int64_t info[8])
+{
+    if (!b || !info) return fail(DRT_ERR_INVALID, "drt_bvh_info: null argument");
+    info[0] = b->nF; info[1] = b->nV; info[2] = b->nF > 1 ? b->nF - 1 : (b->nF == 1 ? 1 : 0);
+    info[3] = b->built ? 1 : 0;
+    info[4] = info[2] * (int64_t)(kNodeQuads * sizeof(float4));
+    info[5] = (int64_t)b->nF * (int64_t)(kTriQuads * sizeof(float4));
+    info[6] = b->builds; info[7] = b->refits;
+    return DRT_OK;
+}
+
+int drt_bvh_bad_indices(const drt_bvh* b, void* stream, int* out)
+{
+    if (!b || !out) return fail(DRT_ERR_INVALID, "drt_bvh_bad_indices: null argument");
+    DeviceGuard g(b->device);
+    CU(cudaMemcpyAsync(out, b->scene + 6, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return DRT_OK;
+}
+
+int drt_closest_hit(const drt_bvh* b, const float* ray6, int64_t N, float* T, int32_t* ID, int64_t strideT, int64_t strideID, void* stream)
+{
+    if (!b) return fail(DRT_ERR_INVALID, "drt_closest_hit: null handle");
+    if (!b->built) return fail(DRT_ERR_STATE, "drt_closest_hit: no mesh has been set (update_mesh first)");
+    if (N < 0) return fail(DRT_ERR_INVALID, "drt_closest_hit: N < 0");
+    if (N == 0) return DRT_OK;
+    if (!ray6 || !T || !ID) return fail(DRT_ERR_INVALID, "drt_closest_hit: null buffer");
+    if (strideT < 1 || strideID < 1) return fail(DRT_ERR_INVALID, "drt_closest_hit: strides must be >= 1");
+    if (((uintptr_t)ray6 & 7u) != 0) return fail(DRT_ERR_INVALID, "drt_closest_hit: ray6 must be 8-byte aligned");
+    DeviceGuard g(b->device);
+    int grid = (int)std::min<int64_t>(blocks_for(N, 256), (int64_t)b->sm_count * 32);
+    closest_hit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(b->view(), ray6, N, T, ID, strideT, strideID);
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_trace_fwd(const drt_bvh* b, const double* V64, const double* origin, const double* dir, int64_t N, double ext_ior,
+                  double int_ior, double* out_ori, double* out_dir, uint8_t* mask3, int32_t* rec_tri1, int32_t* rec_tri2,
+                  uint8_t* hit1, void* stream)
+{
+    if (!b) return fail(DRT_ERR_INVALID, "drt_trace_fwd: null handle");
+    if (!b->built) return fail(DRT_ERR_STATE, "drt_trace_fwd: no mesh has been set (update_mesh first)");
+    if (N < 0) return fail(DRT_ERR_INVALID, "drt_trace_fwd: N < 0");
+    if (N == 0) return DRT_OK;
+    if (!origin || !dir || !out_ori || !out_dir || !mask3) return fail(DRT_ERR_INVALID, "drt_trace_fwd: null buffer");
+    if (b->nF > 0 && !V64) return fail(DRT_ERR_INVALID, "drt_trace_fwd: V64 is null");
+    if ((rec_tri1 == nullptr) != (rec_tri2 == nullptr)) return fail(DRT_ERR_INVALID, "drt_trace_fwd: rec_tri1/rec_tri2 must both be given or both be null");
+    DeviceGuard g(b->device);
+    int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
+    trace_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir,
+                                                              mask3, rec_tri1, rec_tri2, hit1);
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_trace_bwd(const drt_bvh* b, const double* V64, const double* origin, const double* dir, int64_t N, double ext_ior,
+                  double int_ior, const int32_t* rec_tri1, const int32_t* rec_tri2, const double* g_out_ori,
+                  const double* g_out_dir, double* grad_V, void* stream)
+{
+    if (!b) return fail(DRT_ERR_INVALID, "drt_trace_bwd: null handle");
+    if (!b->built) return fail(DRT_ERR_STATE, "drt_trace_bwd: no mesh has been set (update_mesh first)");
+    if (N < 0) return fail(DRT_ERR_INVALID, "drt_trace_bwd: N < 0");
+    if (N == 0 || b->nF == 0) return DRT_OK;
+    if (!V64 || !origin || !dir || !rec_tri1 || !rec_tri2 || !g_out_dir || !grad_V) return fail(DRT_ERR_INVALID, "drt_trace_bwd: null buffer");
+    DeviceGuard g(b->device);
+    int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
+    trace_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, rec_tri1, rec_tri2,
+                                                              g_out_ori, g_out_dir, grad_V);
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_ray_loss_grad(const double* out_ori, const double* out_dir, const uint8_t* mask3, const double* screen,
+                      const uint8_t* valid, int64_t N, double* g_out_dir, double* loss_sum, void* stream)
+{
+    if (N < 0) return fail(DRT_ERR_INVALID, "drt_ray_loss_grad: N < 0");
+    if (N == 0) return DRT_OK;
+    if (!out_ori || !out_dir || !mask3 || !screen || !g_out_dir) return fail(DRT_ERR_INVALID, "drt_ray_loss_grad: null buffer");
+    int dev = 0, sms = 148;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int grid = (int)std::min<int64_t>(blocks_for(N, 256), (int64_t)sms * 16);
+    ray_loss_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_ori, out_dir, mask3, screen, valid, N, g_out_dir, loss_sum);
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+}  // extern "C"

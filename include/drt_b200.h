@@ -1,0 +1,135 @@
+/*
+ * drt_b200.h -- C ABI of the B200-native refraction tracer (libdrt_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of lvjiahui/DRT: the ray-query plugin
+ * `optix_mesh` (reference optix_extend.cpp:6-83, OptiX Prime closest-hit) and the per-ray
+ * two-bounce refraction chain + its autograd backward (reference DiffRender.py:420-432, 492-546;
+ * optim.py:210).  Plain pointers and sizes only; no torch, no C++ types.  All pointers are DEVICE
+ * pointers on the device the handle was created for, unless stated otherwise; `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Every call is asynchronous with
+ * respect to the host and ordered on `stream`.
+ *
+ * Return value: 0 on success, non-zero error code otherwise; drt_last_error() gives the text of
+ * the last error raised on the calling thread.  No exceptions cross this boundary (the reference
+ * plugin aborts through C assert / C++ exceptions: optix_extend.cpp:17-18,25,30-31).
+ */
+#ifndef DRT_B200_H
+#define DRT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DRT_API __attribute__((visibility("default")))
+#else
+#define DRT_API
+#endif
+
+#define DRT_OK 0
+#define DRT_ERR_INVALID 1 /* bad argument (null pointer, negative size, index out of range flag) */
+#define DRT_ERR_CUDA 2    /* a CUDA runtime call failed; see drt_last_error() */
+#define DRT_ERR_STATE 3   /* query before any build (reference: assert(builded), optix_extend.cpp:30) */
+
+typedef struct drt_bvh drt_bvh;
+
+/* Replaces optix_mesh::optix_mesh(unsigned cuda_device) -- optix_extend.cpp:8-12. */
+DRT_API int drt_bvh_create(int device, drt_bvh** out);
+DRT_API int drt_bvh_destroy(drt_bvh* bvh);
+
+/*
+ * Replaces optix_mesh::update_mesh(F, V) -- optix_extend.cpp:14-21,61-67: set triangles and
+ * (re)build the acceleration structure from scratch (LBVH: Morton codes + radix sort + Karras
+ * hierarchy + bottom-up fit).  F int32[nF,3], V32 float32[nV,3], contiguous.  The handle keeps its
+ * OWN device copies, so the caller's buffers may be freed after the call is enqueued (the
+ * reference instead retains the tensors, optix_extend.cpp:15-16,70-71).
+ * The build is enqueued on `stream`; later queries on the same stream see it (the reference's
+ * update(RTP_MODEL_HINT_ASYNC) + finish() pair, optix_extend.cpp:32,66).
+ */
+DRT_API int drt_bvh_build(drt_bvh* bvh, const int32_t* F, int32_t nF, const float* V32, int32_t nV, void* stream);
+
+/* Same, taking the float64 vertices of Scene.vertices and doing the float32 cast of
+ * DiffRender.py:311,379 on the device (round-to-nearest-even, identical to tensor.to(float32)). */
+DRT_API int drt_bvh_build_f64(drt_bvh* bvh, const int32_t* F, int32_t nF, const double* V64, int32_t nV, void* stream);
+
+/*
+ * Replaces optix_mesh::update_vert(V) -- optix_extend.cpp:23-27: new vertex positions, previous
+ * faces.  `refit` = 0 rebuilds from scratch like the reference does every iteration
+ * (DiffRender.py:379-380); `refit` = 1 keeps the tree topology and only refits boxes (legal
+ * because topology changes only at update_mesh, optim.py:195).  Exactly one of V32 / V64 non-NULL.
+ */
+DRT_API int drt_bvh_update_vert(drt_bvh* bvh, const float* V32, const double* V64, int32_t nV, int refit, void* stream);
+
+/* Number of face indices that were outside [0,nV) at the last drt_bvh_build (they are clamped so
+ * that no kernel faults; the reference would read out of bounds).  Synchronises `stream`. */
+DRT_API int drt_bvh_bad_indices(const drt_bvh* bvh, void* stream, int* out);
+
+/* info[0]=nF, [1]=nV, [2]=number of BVH nodes, [3]=built flag, [4]=node bytes, [5]=triangle bytes,
+ * [6]=builds so far, [7]=refits so far.  Host call, no device sync. */
+DRT_API int drt_bvh_info(const drt_bvh* bvh, int64_t info[8]);
+
+/*
+ * Replaces optix_mesh::intersect(Ray) -- optix_extend.cpp:29-57 (RTP_QUERY_TYPE_CLOSEST,
+ * RTP_BUFFER_FORMAT_RAY_ORIGIN_DIRECTION in, RTP_BUFFER_FORMAT_HIT_T_TRIID out).
+ * ray6 float32[N,6] = (origin, direction), direction need NOT be unit length (silhouette rays,
+ * DiffRender.py:213-224); tmin = 0, tmax = inf, no culling.
+ * T[i*strideT] = hit distance in units of |direction| (>0), or -1 on a miss; ID[i*strideID] =
+ * triangle index or -1.  Strides are in ELEMENTS; strideT = strideID = 2 with ID = (int32*)T + 1
+ * reproduces the reference's interleaved {float t; int id} hit buffer (optix_extend.cpp:41-56).
+ * Exact closest hit: ties in t resolve to the lowest triangle index.
+ */
+DRT_API int drt_closest_hit(const drt_bvh* bvh, const float* ray6, int64_t N, float* T, int32_t* ID, int64_t strideT,
+                    int64_t strideID, void* stream);
+
+/*
+ * Replaces Scene.render_transparent -- DiffRender.py:420-432 (trace2 :537-546, Dintersect
+ * :492-501, JIT_Dintersect :64-121, refract_ray :503-535, Refract :35-49, FrDielectric :51-61) in
+ * ONE launch: entry hit -> refract -> exit hit -> refract -> occlusion query, per ray.
+ *   V64            float64[nV,3] current vertices (differentiable re-intersection uses these;
+ *                  the queries use the float32 copy the BVH was built from, as the reference does)
+ *   origin, dir    float64[N,3] (cast to float32 for the queries: DiffRender.py:387-388)
+ *   ext_ior/int_ior  DiffRender.py:21 (1.00029) / optim.py:178
+ *   out_ori,out_dir  float64[N,3]; zeros where the ray is not a valid two-bounce path
+ *   mask3          uint8[N,3] (torch.bool layout), all three columns equal (DiffRender.py:423,431)
+ *   rec_tri1/2     int32[N] hit records for drt_trace_bwd: triangle ids of hit 1 / hit 2, -1 where
+ *                  the path is invalid.  May be NULL (inference only).
+ *   hit1           optional uint8[N]: 1 where the primary ray hits anything = Scene.render_mask
+ *                  (DiffRender.py:434-438) as a by-product.  May be NULL.
+ */
+DRT_API int drt_trace_fwd(const drt_bvh* bvh, const double* V64, const double* origin, const double* dir, int64_t N,
+                  double ext_ior, double int_ior, double* out_ori, double* out_dir, uint8_t* mask3,
+                  int32_t* rec_tri1, int32_t* rec_tri2, uint8_t* hit1, void* stream);
+
+/*
+ * Replaces loss.backward() through the autograd graph of the chain above (optim.py:210): replays
+ * the cached hit records, evaluates the analytic Jacobian of (out_ori, out_dir) w.r.t. the six
+ * hit-triangle vertices in float64 and scatter-adds into grad_V.
+ *   g_out_ori      float64[N,3] upstream gradient of out_ori, or NULL (= zeros; optim.py:100)
+ *   g_out_dir      float64[N,3] upstream gradient of out_dir
+ *   grad_V         float64[nV,3], ACCUMULATED into (caller zeroes) -- index_put_(accumulate=True)
+ */
+DRT_API int drt_trace_bwd(const drt_bvh* bvh, const double* V64, const double* origin, const double* dir, int64_t N,
+                  double ext_ior, double int_ior, const int32_t* rec_tri1, const int32_t* rec_tri2,
+                  const double* g_out_ori, const double* g_out_dir, double* grad_V, void* stream);
+
+/*
+ * Fused consumer (reference optim.py:96-106, Loss_calculator.ray_loss): upstream gradient of
+ *   loss = sum_{valid & mask} || out_dir - normalize(screen - out_ori.detach()) ||^2
+ * written as g_out_dir = 2*(out_dir - target) where valid&mask else 0, and the loss value
+ * accumulated into loss_sum[0] (float64, caller zeroes).  valid uint8[N] may be NULL (= all true).
+ */
+DRT_API int drt_ray_loss_grad(const double* out_ori, const double* out_dir, const uint8_t* mask3, const double* screen,
+                      const uint8_t* valid, int64_t N, double* g_out_dir, double* loss_sum, void* stream);
+
+/* Text of the last error on this thread ("" if none).  Never NULL. */
+DRT_API const char* drt_last_error(void);
+
+/* Library/ABI version: major*1000 + minor. */
+DRT_API int drt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRT_B200_H */

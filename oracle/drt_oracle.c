@@ -207,23 +207,23 @@ ORC_API void orc_bvh_free(orc_bvh* B)
 
 ORC_API int32_t orc_bvh_num_nodes(const orc_bvh* B) { return B->n_nodes; }
 
-/* conservative slab test in double on the float box (tiny relative slack so that the exact
-   triangle test, not the box test, decides every hit) */
+/* Slab test in double on the float box, closed-box semantics.  Near/far planes are chosen by the
+   sign of the direction; a zero direction component gives +-inf (origin strictly inside/outside
+   the slab) or NaN (origin exactly on a slab plane), and fmax/fmin drop the NaN = "no constraint",
+   which is the correct answer for a ray travelling inside a face plane.  The 1e-9 slack makes the
+   exact triangle test, never the box test, decide every hit. */
 static inline int box_test(const orc_node* nd, d3 o, d3 inv, double tbest, double* tnear)
 {
     double t0 = 0.0, t1 = tbest;
     const double oo[3] = {o.x, o.y, o.z}, ii[3] = {inv.x, inv.y, inv.z};
     for (int k = 0; k < 3; ++k) {
-        double a = ((double)nd->lo[k] - oo[k]) * ii[k];
-        double b = ((double)nd->hi[k] - oo[k]) * ii[k];
-        double mn = a < b ? a : b, mx = a < b ? b : a;
-        if (mn != mn) mn = -INFINITY; /* 0*inf: origin on a slab plane of a parallel ray */
-        if (mx != mx) mx = INFINITY;
-        if (mn > t0) t0 = mn;
-        if (mx < t1) t1 = mx;
+        int neg = signbit(ii[k]);
+        double pn = (double)(neg ? nd->hi[k] : nd->lo[k]), pf = (double)(neg ? nd->lo[k] : nd->hi[k]);
+        t0 = fmax(t0, (pn - oo[k]) * ii[k]);
+        t1 = fmin(t1, (pf - oo[k]) * ii[k]);
     }
     *tnear = t0;
-    return t0 * (1.0 - 1e-9) - 1e-300 <= t1 * (1.0 + 1e-9);
+    return t0 * (1.0 - 1e-9) <= t1 * (1.0 + 1e-9);
 }
 
 typedef struct { int64_t nodes, tris; } orc_counters;
