@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- primary rays/s forward+backward of the refraction hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C4] [--impl reference]
+
+A step = one optim.py-shaped ray iteration over the whole view set of the config:
+    Scene.update_verticex (BVH rebuild, DiffRender.py:378-380)  ->  Scene.render_transparent (fused
+    forward kernel)  ->  ray_loss gradient (optim.py:96-106)  ->  backward kernel  ->  [N>1: NCCL
+    all-reduce of grad_V].  Views are sharded over ranks (view k -> rank k mod N), mesh/BVH replicated.
+
+`value`   : inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`     : the same step through the public Scene API with HOST (pinned) ray buffers: per view
+            H2D of origin/ray_dir/screen/valid, D2H of grad_V + loss, copies inside the timed region.
+`roofline`: dominant kernel (fused forward) -- algorithmic bytes (profiles/canonical_counters.json,
+            frozen from the CPU oracle's canonical-LBVH counters) / CUDA-event kernel time, against
+            MEASURED_PEAKS.json's HBM copy bandwidth.
+`cpu_baseline` / `--impl reference`: the CPU oracle port (oracle/drt_oracle.c, OpenMP, all host
+            threads) on a bounded sample of the same workload.  DRT has no CPU path of its own and
+            its GPU path needs OptiX Prime 6.5 (absent, unsupported on Blackwell).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "primary rays/s fwd+bwd"
+UNIT = "rays/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C4", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--views", type=int, default=0, help="override the number of views (debug)")
+    ap.add_argument("--ref-views", type=int, default=8, help="views per step of the CPU reference arm")
+    ap.add_argument("--cpu-views", type=int, default=36, help="views of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--refit", action="store_true", help="refit instead of rebuilding the BVH each step")
+    return ap.parse_args()
+
+
+def workload_name(cfg, n_views):
+    return f"{cfg['name']}: {cfg['desc'].split(',')[0]}, {n_views} views {cfg['resx']}x{cfg['resy']}"
+
+
+def load_counters(name):
+    p = os.path.join(ROOT, "profiles", "canonical_counters.json")
+    try:
+        return json.load(open(p))[name]
+    except Exception:
+        return None
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on host cores (cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------
+def cpu_step(cfg, cams, g_seed=0):
+    """One pass of the hot path on the CPU oracle over the rays of `cams`: BVH build, forward,
+    ray_loss-shaped upstream gradient, backward.  -> (n_rays, seconds)"""
+    import numpy as np
+    from drt_b200 import configs, views
+    from oracle import oracle
+    rays = [views.generate_ray(cfg["resy"], cfg["resx"], c[3], c[2]) for c in cams]
+    o = np.concatenate([r[0].numpy() for r in rays])
+    d = np.concatenate([r[1].numpy() for r in rays])
+    rng = np.random.default_rng(g_seed)
+    target = rng.standard_normal((len(o), 3))
+    t0 = time.perf_counter()
+    m = oracle.OracleMesh(cfg["vertices"], cfg["faces"])
+    q = m.trace_fwd(o, d, configs.INT_IOR)
+    g_dir = 2.0 * (q["out_dir"] - target) * q["mask"]
+    m.trace_bwd(o, d, q["tri1"], q["tri2"], None, g_dir, configs.INT_IOR)
+    return len(o), time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from drt_b200 import configs
+    from oracle import oracle
+    cfg = configs.make(args.config)
+    nv = max(1, min(args.ref_views, cfg["n_views"]))
+    stride = max(1, cfg["n_views"] // nv)
+    cams = cfg["cams"][::stride][:nv]
+    for _ in range(args.warmup):
+        cpu_step(cfg, cams)
+    t, n = 0.0, 0
+    for _ in range(args.steps):
+        nr, dt = cpu_step(cfg, cams)
+        t += dt
+        n += nr
+    val = n / t
+    sample = f"{nv} of {cfg['n_views']} views per step ({n // args.steps} rays), oracle/drt_oracle.c canonical-LBVH path"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, cfg["n_views"]), "device": "host CPU"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (pynvml; the recipe's nvidia-smi query, in-process)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.active = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._halt.is_set():
+            if self.active:
+                try:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    for bit, name in self.REASONS.items():
+                        if r & bit and name != "gpu_idle":
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import drt_b200.DiffRender as R
+    from drt_b200 import _lib, configs, dist as ddist, views
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: drt_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    cfg = configs.make(args.config)
+    if args.views:
+        cfg["cams"] = cfg["cams"][:args.views]
+        cfg["n_views"] = len(cfg["cams"])
+    n_views, resy, resx = cfg["n_views"], cfg["resy"], cfg["resx"]
+    n_pix = resy * resx
+    mine = ddist.shard_views(n_views, rank, world)
+    cams = [cfg["cams"][k] for k in mine]
+    n_local = len(cams) * n_pix
+    n_total = n_views * n_pix
+
+    R.intIOR = configs.INT_IOR
+    scene = R.Scene(vertices=cfg["vertices"], faces=cfg["faces"], cuda_device=local)
+    scene.refit = bool(args.refit)
+    V = scene.vertices.clone().requires_grad_(True)
+    nV = V.shape[0]
+
+    # ---- synthetic inputs: rays of my views (device + pinned host copies), screen targets ----
+    origin, ray_dir = views.view_batch(cams, resy, resx, device=dev)
+    tgt_scene = R.Scene(vertices=configs.perturbed_target_mesh(cfg["vertices"]), faces=cfg["faces"], cuda_device=local)
+    with torch.no_grad():
+        t_ori, t_dir, t_mask = tgt_scene.render_transparent(origin, ray_dir)
+        screen = (t_ori + 100.0 * t_dir).contiguous()      # a measured 3-D screen point per pixel (optim.py:96)
+        valid = t_mask[:, 0].contiguous()
+    del tgt_scene, t_ori, t_dir, t_mask
+    g_dir = torch.empty_like(origin)
+    loss_buf = torch.zeros(1, dtype=torch.float64, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    stream_ptr = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)  # noqa: E731
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def step(o, d, scr, val, gd, marks=None):
+        """One ray iteration over rays (o, d) resident on the device."""
+        V.grad = None
+        if marks is not None: marks[0].record()
+        scene.update_verticex(V)                                     # BVH rebuild
+        if marks is not None: marks[1].record()
+        out_ori, out_dir, mask = scene.render_transparent(o, d)      # fused forward kernel
+        if marks is not None: marks[2].record()
+        _lib.call("drt_ray_loss_grad", p(out_ori), p(out_dir), p(mask), p(scr), p(val), o.shape[0], p(gd), p(loss_buf),
+                  stream_ptr())
+        if marks is not None: marks[3].record()
+        out_dir.backward(gd)                                         # backward kernel -> V.grad
+        if marks is not None: marks[4].record()
+        return mask
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- value: HBM-resident, K timed steps -------------------------------------------------
+    mask = None
+    for _ in range(args.warmup):
+        loss_buf.zero_()
+        mask = step(origin, ray_dir, screen, valid, g_dir)
+        if world > 1:
+            ddist.allreduce_grad(V.grad)
+    sync_all()
+    cov_hit = None
+    valid_frac = float(mask[:, 0].float().mean().item()) if n_local else 0.0
+    sampler = ClockSampler(local)
+    sampler.start()
+    marks = [[ev() for _ in range(6)] for _ in range(args.steps)]
+    launches0 = lib.drt_kernel_launches()
+    sync_all()
+    sampler.active = True
+    t_wall0 = time.perf_counter()
+    start, end = ev(), ev()
+    start.record()
+    for k in range(args.steps):
+        loss_buf.zero_()
+        step(origin, ray_dir, screen, valid, g_dir, marks[k])
+        if world > 1:
+            ddist.allreduce_grad(V.grad)
+        marks[k][5].record()
+    end.record()
+    torch.cuda.synchronize(dev)
+    sampler.active = False
+    t_wall = time.perf_counter() - t_wall0
+    launches = lib.drt_kernel_launches() - launches0
+    sync_all()
+    t_total_ms = start.elapsed_time(end)
+    phases = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / args.steps for i in range(5)]
+    tt = torch.tensor([t_total_ms, phases[1], phases[3], phases[0], phases[4]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_total_ms, t_fwd_ms, t_bwd_ms, t_build_ms, t_ar_ms = tt.tolist()
+    ms_per_step = t_total_ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+    loss_val = float(loss_buf.item())
+    grad_norm = float(V.grad.norm().item())
+
+    # ---- e2e: host buffers, copies inside the timed region ----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = [t.cpu().pin_memory() for t in (origin, ray_dir, screen, valid)]
+        del origin, ray_dir, screen, valid, g_dir
+        torch.cuda.empty_cache()
+        nbuf = 2
+        bufs = [[torch.empty((n_pix,) + h.shape[1:], dtype=h.dtype, device=dev) for h in host] for _ in range(nbuf)]
+        gds = [torch.empty((n_pix, 3), dtype=torch.float64, device=dev) for _ in range(nbuf)]
+        copy_stream = torch.cuda.Stream(dev)
+        ready = [torch.cuda.Event() for _ in range(nbuf)]
+        free = [torch.cuda.Event() for _ in range(nbuf)]
+        grad_host = torch.empty((nV, 3), dtype=torch.float64).pin_memory()
+        loss_host = torch.empty(1, dtype=torch.float64).pin_memory()
+        main = torch.cuda.current_stream(dev)
+
+        def e2e_step():
+            V.grad = None
+            loss_buf.zero_()
+            scene.update_verticex(V)
+            for j in range(len(cams)):
+                b = j % nbuf
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(free[b])            # the compute that last used this buffer is done
+                    for dst, src in zip(bufs[b], host):
+                        dst.copy_(src[j * n_pix:(j + 1) * n_pix], non_blocking=True)
+                    ready[b].record(copy_stream)
+                main.wait_event(ready[b])
+                o, d, scr, val = bufs[b]
+                out_ori, out_dir, mask = scene.render_transparent(o, d)
+                _lib.call("drt_ray_loss_grad", p(out_ori), p(out_dir), p(mask), p(scr), p(val), n_pix, p(gds[b]), p(loss_buf),
+                          stream_ptr())
+                out_dir.backward(gds[b])
+                free[b].record(main)
+            if world > 1:
+                ddist.allreduce_grad(V.grad)
+            grad_host.copy_(V.grad, non_blocking=True)
+            loss_host.copy_(loss_buf, non_blocking=True)
+            main.synchronize()                                  # the result is on the host
+
+        for b in range(nbuf):
+            free[b].record(main)
+        for _ in range(max(1, min(args.warmup, 3))):
+            e2e_step()
+        sync_all()
+        k_e2e = max(3, min(args.steps, 10))
+        s2, e2 = ev(), ev()
+        s2.record()
+        for _ in range(k_e2e):
+            e2e_step()
+        e2.record()
+        torch.cuda.synchronize(dev)
+        te = torch.tensor([s2.elapsed_time(e2)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = te.item() / k_e2e
+        e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": k_e2e,
+               "h2d_bytes_per_step": int(n_total * (24 + 24 + 24 + 1)), "d2h_bytes_per_step": int(world * (nV * 24 + 8)),
+               "note": "per-view H2D of origin/ray_dir/screen/valid from pinned host memory, double-buffered on a copy stream; "
+                       "D2H of grad_V and loss; through Scene.update_verticex/render_transparent/backward"}
+        assert abs(loss_host.item() - loss_val) <= 1e-6 * max(1.0, abs(loss_val)), (loss_host.item(), loss_val)
+    sampler.stop()
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        nvb = max(1, min(args.cpu_views, n_views))
+        stride = max(1, n_views // nvb)
+        ccams = cfg["cams"][::stride][:nvb]
+        cpu_step(cfg, ccams[:1])  # warm
+        nr, dt = cpu_step(cfg, ccams)
+        cpu = {"value": nr / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+               "sample": f"{nvb} of {n_views} views ({nr} rays) in {dt:.2f} s, oracle/drt_oracle.c (canonical LBVH, OpenMP)"}
+
+    if rank == 0:
+        cnt = load_counters(cfg["name"])
+        peak, peak_src = measured_peak()
+        roof = None
+        if cnt:
+            b_fwd = cnt["bytes_per_ray"]["fwd"]
+            b_tot = cnt["bytes_per_ray"]["total"]
+            ach = b_fwd * (n_total / world) / (t_fwd_ms * 1e-3) / 1e9
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["trace_fwd"]["dram_bytes_per_launch"]
+            except Exception:
+                pass
+            roof = {"bound": "hbm", "kernel": "trace_fwd_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peak_src, "bytes_per_ray_fwd": b_fwd, "bytes_per_ray_total": b_tot,
+                    "kernel_ms": t_fwd_ms, "rays_per_launch": n_total // world,
+                    "step_frac": (b_tot * (n_total / world) / ((t_fwd_ms + t_bwd_ms) * 1e-3) / 1e9) / peak,
+                    "model": "no-cache traversal bytes on the canonical LBVH (profiles/canonical_counters.json)"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(cfg, n_views), "rays_per_step": n_total, "views_per_gpu": len(cams),
+                       "parallelism": f"views sharded over {world} GPU(s), mesh/BVH replicated, 1 all-reduce of grad_V",
+                       "bvh": "refit each step" if args.refit else "full LBVH rebuild each step",
+                       "l2": "inputs larger than L2 (%.1f GB of rays per step per GPU)" % (n_local * 48 / 1e9),
+                       "int_ior": configs.INT_IOR, "valid_frac_rank0": valid_frac},
+            "phases_ms": {"bvh_build": t_build_ms, "fwd": t_fwd_ms, "loss_grad": phases[2], "bwd": t_bwd_ms, "allreduce": t_ar_ms},
+            "wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary(), "loss": loss_val, "grad_norm": grad_norm,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

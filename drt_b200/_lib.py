@@ -12,6 +12,7 @@ _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 SIGNATURES = {
     "drt_version": (C.c_int, []),
     "drt_last_error": (C.c_char_p, []),
+    "drt_kernel_launches": (C.c_uint64, []),
     "drt_bvh_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "drt_bvh_destroy": (C.c_int, [_vp]),
     "drt_bvh_build": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),

@@ -13,6 +13,7 @@ using namespace drt;
 namespace {
 
 thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;  // kernels of this library launched so far (bench.py's gpu_launches)
 
 int fail(int code, const char* fmt, ...)
 {
@@ -113,9 +114,9 @@ int fit_and_emit(drt_bvh* b, cudaStream_t st)
     if (n <= 0) return DRT_OK;
     if (n > 1) CU(cudaMemsetAsync(b->flags, 0, sizeof(int) * (size_t)(n - 1), st));
     fit_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_vals, n, b->children, b->parent, b->blo, b->bhi,
-                                                    b->flags);
-    emit_nodes_kernel<<<blocks_for(n > 1 ? n - 1 : 1, 256), 256, 0, st>>>(n, b->children, b->blo, b->bhi, b->nodes);
-    emit_tris_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_vals, n, b->tris);
+                                                    b->flags); ++g_launches;
+    emit_nodes_kernel<<<blocks_for(n > 1 ? n - 1 : 1, 256), 256, 0, st>>>(n, b->children, b->blo, b->bhi, b->nodes); ++g_launches;
+    emit_tris_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_vals, n, b->tris); ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
 }
@@ -137,9 +138,9 @@ int build_tree(drt_bvh* b, cudaStream_t st)
     if ((rc = ensure(b->nodes, b->capN, (size_t)kNodeQuads * (size_t)(n > 1 ? n - 1 : 1)))) return rc;
     if ((rc = ensure(b->tris, b->capT, (size_t)kTriQuads * (size_t)n))) return rc;
 
-    init_scene_kernel<<<1, 32, 0, st>>>(b->scene, false);
-    centroid_bounds_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene);
-    morton_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene, b->keys, b->vals);
+    init_scene_kernel<<<1, 32, 0, st>>>(b->scene, false); ++g_launches;
+    centroid_bounds_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene); ++g_launches;
+    morton_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene, b->keys, b->vals); ++g_launches;
     // (code, id) pairs: LSD radix sort over the 63 live key bits
     cub::DoubleBuffer<uint64_t> dk(b->keys, b->keys + n);
     cub::DoubleBuffer<uint32_t> dv(b->vals, b->vals + n);
@@ -154,9 +155,12 @@ int build_tree(drt_bvh* b, cudaStream_t st)
     }
     size_t tmp_bytes = b->cub_bytes;
     CU(cub::DeviceRadixSort::SortPairs(b->cub_tmp, tmp_bytes, dk, dv, n, 0, 63, st));
+    g_launches += 1;  // the sort is counted as ONE launch (its internal passes are CUB's)
     b->sorted_vals = dv.Current();
-    if (n > 1)
+    if (n > 1) {
         topology_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>(dk.Current(), n, b->children, b->parent);
+        ++g_launches;
+    }
     CU(cudaGetLastError());
     return fit_and_emit(b, st);
 }
@@ -168,7 +172,10 @@ int set_vertices(drt_bvh* b, const float* V32, const double* V64, int nV, cudaSt
     b->nV = nV;
     if (nV <= 0) return DRT_OK;
     if (V32) CU(cudaMemcpyAsync(b->V32, V32, sizeof(float) * 3 * (size_t)nV, cudaMemcpyDeviceToDevice, st));
-    else cast_vertices_kernel<<<blocks_for(3 * (int64_t)nV, 256), 256, 0, st>>>(V64, b->V32, 3 * nV);
+    else {
+        cast_vertices_kernel<<<blocks_for(3 * (int64_t)nV, 256), 256, 0, st>>>(V64, b->V32, 3 * nV);
+        ++g_launches;
+    }
     CU(cudaGetLastError());
     return DRT_OK;
 }
@@ -186,8 +193,11 @@ int build_common(drt_bvh* b, const int32_t* F, int nF, const float* V32, const d
     if ((rc = set_vertices(b, V32, V64, nV, st))) return rc;
     if ((rc = ensure(b->F, b->capF, 3 * (size_t)(nF > 0 ? nF : 1)))) return rc;
     b->nF = nF;
-    init_scene_kernel<<<1, 32, 0, st>>>(b->scene, true);
-    if (nF > 0) copy_faces_kernel<<<blocks_for(3 * (int64_t)nF, 256), 256, 0, st>>>(F, b->F, 3 * nF, nV, (int*)(b->scene + 6));
+    init_scene_kernel<<<1, 32, 0, st>>>(b->scene, true); ++g_launches;
+    if (nF > 0) {
+        copy_faces_kernel<<<blocks_for(3 * (int64_t)nF, 256), 256, 0, st>>>(F, b->F, 3 * nF, nV, (int*)(b->scene + 6));
+        ++g_launches;
+    }
     CU(cudaGetLastError());
     return build_tree(b, st);
 }
@@ -197,6 +207,8 @@ int build_common(drt_bvh* b, const int32_t* F, int nF, const float* V32, const d
 extern "C" {
 
 int drt_version(void) { return 1000; }
+
+unsigned long long drt_kernel_launches(void) { return g_launches; }
 
 const char* drt_last_error(void) { return g_err; }
 
@@ -290,7 +302,7 @@ int drt_closest_hit(const drt_bvh* b, const float* ray6, int64_t N, float* T, in
     if (((uintptr_t)ray6 & 7u) != 0) return fail(DRT_ERR_INVALID, "drt_closest_hit: ray6 must be 8-byte aligned");
     DeviceGuard g(b->device);
     int grid = (int)std::min<int64_t>(blocks_for(N, 256), (int64_t)b->sm_count * 32);
-    closest_hit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(b->view(), ray6, N, T, ID, strideT, strideID);
+    closest_hit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(b->view(), ray6, N, T, ID, strideT, strideID); ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
 }
@@ -309,7 +321,7 @@ int drt_trace_fwd(const drt_bvh* b, const double* V64, const double* origin, con
     DeviceGuard g(b->device);
     int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
     trace_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir,
-                                                              mask3, rec_tri1, rec_tri2, hit1);
+                                                              mask3, rec_tri1, rec_tri2, hit1); ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
 }
@@ -326,7 +338,7 @@ int drt_trace_bwd(const drt_bvh* b, const double* V64, const double* origin, con
     DeviceGuard g(b->device);
     int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
     trace_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, rec_tri1, rec_tri2,
-                                                              g_out_ori, g_out_dir, grad_V);
+                                                              g_out_ori, g_out_dir, grad_V); ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
 }
@@ -341,7 +353,7 @@ int drt_ray_loss_grad(const double* out_ori, const double* out_dir, const uint8_
     CU(cudaGetDevice(&dev));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int grid = (int)std::min<int64_t>(blocks_for(N, 256), (int64_t)sms * 16);
-    ray_loss_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_ori, out_dir, mask3, screen, valid, N, g_out_dir, loss_sum);
+    ray_loss_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_ori, out_dir, mask3, screen, valid, N, g_out_dir, loss_sum); ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
 }

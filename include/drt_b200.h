@@ -126,6 +126,9 @@ DRT_API int drt_ray_loss_grad(const double* out_ori, const double* out_dir, cons
 /* Text of the last error on this thread ("" if none).  Never NULL. */
 DRT_API const char* drt_last_error(void);
 
+/* Number of kernels this library has launched in this process (monotonic; for bench accounting). */
+DRT_API unsigned long long drt_kernel_launches(void);
+
 /* Library/ABI version: major*1000 + minor. */
 DRT_API int drt_version(void);
 
