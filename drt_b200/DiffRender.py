@@ -65,22 +65,25 @@ class RefractTrace(torch.autograd.Function):
         out_ori = torch.empty((n, 3), dtype=torch.float64, device=dev)
         out_dir = torch.empty((n, 3), dtype=torch.float64, device=dev)
         mask = torch.empty((n, 3), dtype=torch.bool, device=dev)
-        rec = torch.empty((2, n), dtype=torch.int32, device=dev)
+        # compact hit records (ray, tri1, tri2, 0) of the valid paths + their count, for backward
+        need_rec = vertices.requires_grad
+        rec = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev) if need_rec else None
+        rec_count = torch.empty(1, dtype=torch.int32, device=dev) if need_rec else None
         st = optix._stream_ptr(dev)
         _lib.call("drt_trace_fwd", mesh._h, _ptr(V), _ptr(o), _ptr(d), n, float(ext_ior), float(int_ior), _ptr(out_ori),
-                  _ptr(out_dir), _ptr(mask), _ptr(rec[0]), _ptr(rec[1]), C.c_void_p(0), st)
+                  _ptr(out_dir), _ptr(mask), _ptr(rec), _ptr(rec_count), C.c_void_p(0), st)
         ctx.mesh = mesh
         ctx.iors = (float(ext_ior), float(int_ior))
-        ctx.save_for_backward(V, o, d, rec)
+        ctx.save_for_backward(V, o, d, rec, rec_count)
         ctx.mark_non_differentiable(mask)
         ctx.set_materialize_grads(False)
         return out_ori, out_dir, mask
 
     @staticmethod
     def backward(ctx, g_ori, g_dir, _g_mask):
-        V, o, d, rec = ctx.saved_tensors
+        V, o, d, rec, rec_count = ctx.saved_tensors
         grad_V = torch.zeros_like(V)
-        if g_ori is None and g_dir is None:
+        if (g_ori is None and g_dir is None) or rec is None:
             return grad_V, None, None, None, None, None
         n = o.shape[0]
         if g_dir is None:
@@ -88,8 +91,8 @@ class RefractTrace(torch.autograd.Function):
         g_dir = g_dir.contiguous()
         g_ori = None if g_ori is None else g_ori.contiguous()
         mesh = ctx.mesh
-        _lib.call("drt_trace_bwd", mesh._h, _ptr(V), _ptr(o), _ptr(d), n, ctx.iors[0], ctx.iors[1], _ptr(rec[0]),
-                  _ptr(rec[1]), _ptr(g_ori), _ptr(g_dir), _ptr(grad_V), optix._stream_ptr(mesh.device))
+        _lib.call("drt_trace_bwd", mesh._h, _ptr(V), _ptr(o), _ptr(d), n, ctx.iors[0], ctx.iors[1], _ptr(rec),
+                  _ptr(rec_count), _ptr(g_ori), _ptr(g_dir), _ptr(grad_V), optix._stream_ptr(mesh.device))
         return grad_V, None, None, None, None, None
 
 

@@ -3,10 +3,11 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/drt_b200.h"
-#include "trace.cuh"
+#include "wavefront.cuh"
 
 using namespace drt;
 
@@ -45,6 +46,29 @@ int ensure(T*& p, size_t& cap, size_t need)
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
+constexpr int kWorkSlots = 64;
+
+// tuning knobs (read once): DRT_FWD_KERNEL = wavefront (default) | simple | prof ; DRT_FWD_THRESH = 1..32
+struct Tuning {
+    bool simple_fwd = false;
+    bool prof = false;
+    int thresh = 16;
+    Tuning()
+    {
+        const char* k = getenv("DRT_FWD_KERNEL");
+        if (k && !strcmp(k, "simple")) simple_fwd = true;
+        if (k && !strcmp(k, "prof")) simple_fwd = prof = true;
+
+        const char* t = getenv("DRT_FWD_THRESH");
+        if (t && atoi(t) >= 1 && atoi(t) <= 32) thresh = atoi(t);
+    }
+};
+const Tuning& tuning()
+{
+    static Tuning t;
+    return t;
+}
+
 }  // namespace
 
 struct drt_bvh {
@@ -66,6 +90,11 @@ struct drt_bvh {
     float4* bhi = nullptr;     size_t capBh = 0;
     int* flags = nullptr;      size_t capFl = 0; // nF-1
     unsigned* scene = nullptr;                   // 6 encoded floats + 1 int (bad index count) + pad
+    int4* listA = nullptr;     size_t capLA = 0; // wavefront list L (ray, tri1, tri2, dead) of the rays that hit
+    int4* listB = nullptr;     size_t capLB = 0; // wavefront list M: entries of L that survive both refractions
+    unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
+    int work_slot = 0;
+    int fwd_blocks_per_sm = 0;                   // occupancy of trace_fwd_persistent_kernel
     uint32_t* sorted_vals = nullptr;             // points into vals (which half holds the sorted ids)
     // traversal data
     float4* nodes = nullptr;   size_t capN = 0;
@@ -228,6 +257,9 @@ int drt_bvh_create(int device, drt_bvh** out)
     b->sm_count = prop.multiProcessorCount;
     CU(cudaMalloc(&b->scene, 8 * sizeof(unsigned)));
     CU(cudaMemset(b->scene, 0, 8 * sizeof(unsigned)));
+    CU(cudaMalloc(&b->work, kWorkSlots * sizeof(unsigned long long)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->fwd_blocks_per_sm, wf_q1_kernel, 128, 0));
+    if (b->fwd_blocks_per_sm < 1) b->fwd_blocks_per_sm = 1;
     *out = b;
     return DRT_OK;
 }
@@ -237,7 +269,7 @@ int drt_bvh_destroy(drt_bvh* b)
     if (!b) return DRT_OK;
     DeviceGuard g(b->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {b->F, b->V32, b->keys, b->vals, b->cub_tmp, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
+    void* ptrs[] = {b->listA, b->listB, b->work, b->F, b->V32, b->keys, b->vals, b->cub_tmp, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -307,38 +339,80 @@ int drt_closest_hit(const drt_bvh* b, const float* ray6, int64_t N, float* T, in
     return DRT_OK;
 }
 
-int drt_trace_fwd(const drt_bvh* b, const double* V64, const double* origin, const double* dir, int64_t N, double ext_ior,
-                  double int_ior, double* out_ori, double* out_dir, uint8_t* mask3, int32_t* rec_tri1, int32_t* rec_tri2,
+int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, const double* dir, int64_t N, double ext_ior,
+                  double int_ior, double* out_ori, double* out_dir, uint8_t* mask3, int32_t* rec, int32_t* rec_count,
                   uint8_t* hit1, void* stream)
 {
+    drt_bvh* b = const_cast<drt_bvh*>(b_);
     if (!b) return fail(DRT_ERR_INVALID, "drt_trace_fwd: null handle");
     if (!b->built) return fail(DRT_ERR_STATE, "drt_trace_fwd: no mesh has been set (update_mesh first)");
-    if (N < 0) return fail(DRT_ERR_INVALID, "drt_trace_fwd: N < 0");
+    if (N < 0 || N > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_trace_fwd: N must be in [0, 2^31)");
+    if ((rec == nullptr) != (rec_count == nullptr)) return fail(DRT_ERR_INVALID, "drt_trace_fwd: rec/rec_count must both be given or both be null");
+    if (rec && ((uintptr_t)rec & 15u)) return fail(DRT_ERR_INVALID, "drt_trace_fwd: rec must be 16-byte aligned");
+    DeviceGuard g(b->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rec_count) CU(cudaMemsetAsync(rec_count, 0, sizeof(int32_t), st));
     if (N == 0) return DRT_OK;
     if (!origin || !dir || !out_ori || !out_dir || !mask3) return fail(DRT_ERR_INVALID, "drt_trace_fwd: null buffer");
     if (b->nF > 0 && !V64) return fail(DRT_ERR_INVALID, "drt_trace_fwd: V64 is null");
-    if ((rec_tri1 == nullptr) != (rec_tri2 == nullptr)) return fail(DRT_ERR_INVALID, "drt_trace_fwd: rec_tri1/rec_tri2 must both be given or both be null");
-    DeviceGuard g(b->device);
-    int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
-    trace_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir,
-                                                              mask3, rec_tri1, rec_tri2, hit1); ++g_launches;
+    if (tuning().simple_fwd) {
+        int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
+        if (tuning().prof) {
+            // utilisation probe (debug): 12 counters = {warp iters, lane iters} x {internal, leaf} x 3 queries
+            CU(cudaMemsetAsync(b->work, 0, 12 * sizeof(unsigned long long), st));
+            trace_fwd_kernel<true><<<grid, 128, 0, st>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir, mask3,
+                                                         (int4*)rec, rec_count, hit1, b->work);
+            unsigned long long c[12];
+            CU(cudaMemcpyAsync(c, b->work, sizeof(c), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (int q = 0; q < 3; ++q)
+                fprintf(stderr, "[drt prof] Q%d internal: %llu warp-iters, %.2f lanes/iter | leaf: %llu warp-iters, %.2f lanes/iter\n", q + 1,
+                        c[4 * q], c[4 * q] ? (double)c[4 * q + 1] / c[4 * q] : 0.0, c[4 * q + 2], c[4 * q + 2] ? (double)c[4 * q + 3] / c[4 * q + 2] : 0.0);
+        } else
+            trace_fwd_kernel<false><<<grid, 128, 0, st>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir, mask3,
+                                                          (int4*)rec, rec_count, hit1, nullptr);
+    } else {
+        // production path: wavefront of persistent query kernels (wavefront.cuh)
+        int rc;
+        if ((rc = ensure(b->listA, b->capLA, (size_t)N))) return rc;
+        if ((rc = ensure(b->listB, b->capLB, (size_t)N))) return rc;
+        // per-launch control block: 3 work counters (Q1,Q2,Q3) + countL + countM
+        unsigned long long* ctl = b->work + (size_t)(b->work_slot++ % (kWorkSlots / 4)) * 4;
+        CU(cudaMemsetAsync(ctl, 0, 4 * sizeof(unsigned long long), st));
+        int* countL = (int*)(ctl + 3);
+        int* countM = countL + 1;
+        const int thresh = tuning().thresh;
+        const int pgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * b->fwd_blocks_per_sm);
+        const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
+        EntryJob j1{origin, dir, out_ori, out_dir, mask3, hit1, b->listA, countL};
+        wf_q1_kernel<<<pgrid, 128, 0, st>>>(b->view(), j1, (int)N, ctl + 0, thresh);
+        wf_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, origin, dir, ext_ior, int_ior, out_ori, out_dir, mask3, b->listA, countL);
+        ExitJob j2{out_ori, out_dir, b->listA};
+        wf_q2_kernel<<<pgrid, 128, 0, st>>>(b->view(), j2, countL, ctl + 1, thresh);
+        wf_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, out_ori, out_dir, mask3, b->listA, countL, b->listB, countM);
+        OcclusionJob j3{out_ori, out_dir, mask3, b->listB, (int4*)rec, rec_count};
+        wf_q3_kernel<<<pgrid, 128, 0, st>>>(b->view(), j3, countM, ctl + 2, thresh);
+        g_launches += 4;
+    }
+    ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
 }
 
 int drt_trace_bwd(const drt_bvh* b, const double* V64, const double* origin, const double* dir, int64_t N, double ext_ior,
-                  double int_ior, const int32_t* rec_tri1, const int32_t* rec_tri2, const double* g_out_ori,
+                  double int_ior, const int32_t* rec, const int32_t* rec_count, const double* g_out_ori,
                   const double* g_out_dir, double* grad_V, void* stream)
 {
     if (!b) return fail(DRT_ERR_INVALID, "drt_trace_bwd: null handle");
     if (!b->built) return fail(DRT_ERR_STATE, "drt_trace_bwd: no mesh has been set (update_mesh first)");
     if (N < 0) return fail(DRT_ERR_INVALID, "drt_trace_bwd: N < 0");
     if (N == 0 || b->nF == 0) return DRT_OK;
-    if (!V64 || !origin || !dir || !rec_tri1 || !rec_tri2 || !g_out_dir || !grad_V) return fail(DRT_ERR_INVALID, "drt_trace_bwd: null buffer");
+    if (!V64 || !origin || !dir || !rec || !rec_count || !g_out_dir || !grad_V) return fail(DRT_ERR_INVALID, "drt_trace_bwd: null buffer");
     DeviceGuard g(b->device);
-    int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
-    trace_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, rec_tri1, rec_tri2,
-                                                              g_out_ori, g_out_dir, grad_V); ++g_launches;
+    int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
+    trace_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, ext_ior, int_ior, (const int4*)rec,
+                                                              rec_count, g_out_ori, g_out_dir, grad_V);
+    ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
 }

@@ -1,5 +1,9 @@
 // trace.cuh -- BVH traversal, fused forward tracer, backward kernel (sm_100a).
 #pragma once
+#include <cooperative_groups.h>
+
+#include <climits>
+
 #include "bvh.cuh"
 
 namespace drt {
@@ -35,8 +39,9 @@ __device__ __forceinline__ bool slab(float lx, float ly, float lz, float hx, flo
 // Exact closest hit (ANY = false) or first hit found (ANY = true; only hit/no-hit is meaningful,
 // which is all the reference uses of its third query: DiffRender.py:426-427).
 // Returns triangle id (-1 on miss) and the float64 distance along the float32 ray.
-template <bool ANY>
-__device__ __forceinline__ void traverse(const BvhView& B, const QRay& r, double& t_best, int& id_best)
+template <bool ANY, bool PROF = false>
+__device__ __forceinline__ void traverse(const BvhView& B, const QRay& r, double& t_best, int& id_best,
+                                         unsigned long long* prof = nullptr)
 {
     t_best = INFINITY;
     id_best = -1;
@@ -51,6 +56,10 @@ __device__ __forceinline__ void traverse(const BvhView& B, const QRay& r, double
     int node = 0;
     for (;;) {
         while (node >= 0) {
+            if (PROF) {  // utilisation probe: warp-iterations vs lane-iterations of the internal-node loop
+                unsigned m = __activemask();
+                if ((threadIdx.x & 31) == __ffs(m) - 1) { atomicAdd(prof, 1ull); atomicAdd(prof + 1, (unsigned long long)__popc(m)); }
+            }
             const float4* p = B.nodes + (size_t)node * kNodeQuads;
             float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
             float ta, tb;
@@ -71,6 +80,10 @@ __device__ __forceinline__ void traverse(const BvhView& B, const QRay& r, double
             }
         }
         {
+            if (PROF) {
+                unsigned m = __activemask();
+                if ((threadIdx.x & 31) == __ffs(m) - 1) { atomicAdd(prof + 2, 1ull); atomicAdd(prof + 3, (unsigned long long)__popc(m)); }
+            }
             const float4* p = B.tris + (size_t)(~node) * kTriQuads;
             float4 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
             double t;
@@ -117,16 +130,26 @@ __device__ __forceinline__ void load_tri64(const BvhView& B, const double* __res
     a2 = ld3(V64 + 3 * (size_t)i2);
 }
 
+__device__ __forceinline__ void write_invalid(double* __restrict__ out_ori, double* __restrict__ out_dir,
+                                              uint8_t* __restrict__ mask3, int64_t i)
+{
+    st3(out_ori + 3 * i, mk3(0, 0, 0));
+    st3(out_dir + 3 * i, mk3(0, 0, 0));
+    mask3[3 * i] = 0; mask3[3 * i + 1] = 0; mask3[3 * i + 2] = 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Scene.render_transparent replacement, one launch (DiffRender.py:420-432).  v1: one thread per
 // ray walks the whole path Q1 -> refract -> Q2 -> refract -> Q3.
 // ---------------------------------------------------------------------------------------------
+template <bool PROF>
 __global__ void __launch_bounds__(128) trace_fwd_kernel(BvhView B, const double* __restrict__ V64,
                                                         const double* __restrict__ origin, const double* __restrict__ dir,
                                                         int64_t N, double ext_ior, double int_ior,
                                                         double* __restrict__ out_ori, double* __restrict__ out_dir,
-                                                        uint8_t* __restrict__ mask3, int32_t* __restrict__ rec1,
-                                                        int32_t* __restrict__ rec2, uint8_t* __restrict__ hit1)
+                                                        uint8_t* __restrict__ mask3, int4* __restrict__ rec,
+                                                        int* __restrict__ rec_count, uint8_t* __restrict__ hit1,
+                                                        unsigned long long* __restrict__ prof)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         d3 o = ld3(origin + 3 * i), d = ld3(dir + 3 * i);
@@ -134,20 +157,20 @@ __global__ void __launch_bounds__(128) trace_fwd_kernel(BvhView B, const double*
         int id1, id2 = -1, id3;
         double t;
         bool valid = false;
-        traverse<false>(B, cast_ray(o, d), t, id1);
+        traverse<false, PROF>(B, cast_ray(o, d), t, id1, prof);
         if (id1 >= 0) {
             HitRec h;
             d3 a0, a1, a2, o1, d1;
             load_tri64(B, V64, id1, a0, a1, a2);
             hit_forward(h, o, d, a0, a1, a2, ext_ior, int_ior, o1, d1);
             if (!h.tir) {
-                traverse<false>(B, cast_ray(o1, d1), t, id2);
+                traverse<false, PROF>(B, cast_ray(o1, d1), t, id2, prof + 4);
                 if (id2 >= 0) {
                     d3 o2, d2;
                     load_tri64(B, V64, id2, a0, a1, a2);
                     hit_forward(h, o1, d1, a0, a1, a2, ext_ior, int_ior, o2, d2);
                     if (!h.tir) {
-                        traverse<true>(B, cast_ray(o2, d2), t, id3);
+                        traverse<true, PROF>(B, cast_ray(o2, d2), t, id3, prof + 8);
                         if (id3 < 0) {
                             valid = true;
                             oo = o2;
@@ -161,7 +184,7 @@ __global__ void __launch_bounds__(128) trace_fwd_kernel(BvhView B, const double*
         st3(out_dir + 3 * i, od);
         uint8_t m = valid ? 1 : 0;
         mask3[3 * i] = m; mask3[3 * i + 1] = m; mask3[3 * i + 2] = m;
-        if (rec1) { rec1[i] = valid ? id1 : -1; rec2[i] = valid ? id2 : -1; }
+        if (rec && valid) rec[atomicAdd(rec_count, 1)] = make_int4((int)i, id1, id2, 0);
         if (hit1) hit1[i] = id1 >= 0 ? 1 : 0;
     }
 }
@@ -179,16 +202,16 @@ __device__ __forceinline__ void scatter3(double* __restrict__ gV, int v, d3 g)
 
 __global__ void __launch_bounds__(128) trace_bwd_kernel(BvhView B, const double* __restrict__ V64,
                                                         const double* __restrict__ origin, const double* __restrict__ dir,
-                                                        int64_t N, double ext_ior, double int_ior,
-                                                        const int32_t* __restrict__ rec1, const int32_t* __restrict__ rec2,
+                                                        double ext_ior, double int_ior, const int4* __restrict__ rec,
+                                                        const int* __restrict__ rec_count,
                                                         const double* __restrict__ g_ori, const double* __restrict__ g_dir,
                                                         double* __restrict__ gV)
 {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-        int id1 = __ldg(rec1 + i);
-        if (id1 < 0) continue;
-        int id2 = __ldg(rec2 + i);
-        if (id2 < 0) continue;
+    const int n = __ldg(rec_count);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int4 rc = __ldg(rec + k);
+        const int64_t i = rc.x;
+        const int id1 = rc.y, id2 = rc.z;
         d3 o = ld3(origin + 3 * i), d = ld3(dir + 3 * i);
         HitRec h1, h2;
         d3 a0, a1, a2, o1, d1, o2, d2;

@@ -1,0 +1,326 @@
+// wavefront.cuh -- the production forward tracer: a stage-synchronous wavefront whose three ray
+// queries run as PERSISTENT warps with dynamic work fetch and ballot compaction.
+//
+// Replaces Scene.render_transparent (reference DiffRender.py:420-432; trace2 :537-546).
+//
+//   Q1   entry query over all N rays            -> misses retire (zeros), hits compacted into list L
+//   R1   refraction 1, float64, dense over L    -> refracted ray parked in out_ori/out_dir
+//   Q2   exit query over L                      -> L[k].z = tri2
+//   R2   refraction 2, float64, dense over L    -> exit ray parked; survivors compacted into list M
+//   Q3   occlusion query (any hit) over M       -> mask = 1 + backward record, or zeros
+//
+// Why not one megakernel with one thread per path (trace_fwd_kernel in trace.cuh, kept as the
+// simple variant): measured on B200 it ran its box tests with ~10 of 32 lanes active -- lanes whose
+// query ended early, lanes without a hit and lanes parked at a leaf all idle while the warp's
+// longest traversal finishes.  Here every query kernel is pure traversal: a lane that finishes
+// retires its result with a couple of stores and is refilled from a global work counter (one
+// atomic per warp per batch), and the float64 refraction math runs dense over compacted lists with
+// its own register budget.
+#pragma once
+#include "trace.cuh"
+
+namespace drt {
+
+constexpr int kDone = INT_MIN;
+constexpr int kFetchBatch = 64;
+
+struct Trav {
+    QRay r;
+    float ix, iy, iz;
+    bool nx, ny, nz;
+    float tmax;
+    double t_best;
+    int id_best;
+    int node;
+    int sp;
+};
+
+__device__ __forceinline__ void trav_init(Trav& T, const BvhView& B, d3 o, d3 d)
+{
+    T.r = cast_ray(o, d);
+    T.ix = __fdiv_rn(1.f, T.r.dx); T.iy = __fdiv_rn(1.f, T.r.dy); T.iz = __fdiv_rn(1.f, T.r.dz);
+    T.nx = signbit(T.ix); T.ny = signbit(T.iy); T.nz = signbit(T.iz);
+    T.tmax = INFINITY;
+    T.t_best = INFINITY;
+    T.id_best = -1;
+    T.sp = 0;
+    T.node = B.nTris > 0 ? 0 : kDone;
+}
+
+// one internal node; a leaf reached while the lane still has internal work is POSTPONED into `pend`
+// (one slot) so that the lane keeps stepping with the rest of the warp instead of parking at it
+__device__ __forceinline__ void trav_internal(Trav& T, const BvhView& B, int* stack, int& pend)
+{
+    const float4* p = B.nodes + (size_t)T.node * kNodeQuads;
+    float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+    float ta, tb;
+    bool ha = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T.r, T.ix, T.iy, T.iz, T.nx, T.ny, T.nz, T.tmax, ta);
+    bool hb = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T.r, T.ix, T.iy, T.iz, T.nx, T.ny, T.nz, T.tmax, tb);
+    int ca = __float_as_int(q3.x), cb = __float_as_int(q3.y);
+    int next;
+    if (ha && hb) {
+        bool a_first = ta <= tb;
+        next = a_first ? ca : cb;
+        if (T.sp < kStackDepth) stack[T.sp++] = a_first ? cb : ca;
+    } else if (ha) {
+        next = ca;
+    } else if (hb) {
+        next = cb;
+    } else {
+        next = T.sp ? stack[--T.sp] : kDone;
+    }
+    if (next < 0 && next != kDone && pend == 0 && T.sp > 0) {
+        pend = next;
+        next = stack[--T.sp];
+    }
+    T.node = next;
+}
+
+template <bool ANY>
+__device__ __forceinline__ bool leaf_test(Trav& T, const BvhView& B, int leaf)
+{
+    const float4* p = B.tris + (size_t)(~leaf) * kTriQuads;
+    float4 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
+    const d3 o = mk3((double)T.r.ox, (double)T.r.oy, (double)T.r.oz);
+    const d3 d = mk3((double)T.r.dx, (double)T.r.dy, (double)T.r.dz);
+    double t;
+    if (query_tri(o, d, mk3((double)r0.x, (double)r0.y, (double)r0.z), mk3((double)r0.w, (double)r1.x, (double)r1.y),
+                  mk3((double)r1.z, (double)r1.w, (double)r2.x), t)) {
+        int id = __float_as_int(r2.y);
+        if (t < T.t_best || (t == T.t_best && id < T.id_best)) {
+            T.t_best = t;
+            T.id_best = id;
+            T.tmax = __double2float_ru(t);
+        }
+        return true;
+    }
+    return false;
+}
+
+template <typename Dummy = void>
+__device__ __forceinline__ int warp_append(int* __restrict__ counter, bool pred)
+{
+    // ballot compaction: one atomic per warp, slot = base + rank among the lanes that append
+    namespace cg = cooperative_groups;
+    int slot = -1;
+    if (pred) {
+        cg::coalesced_group g = cg::coalesced_threads();
+        int base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(counter, (int)g.size());
+        slot = g.shfl(base, 0) + (int)g.thread_rank();
+    }
+    return slot;
+}
+
+// Persistent query driver.  Job: bool load(int item, d3& o, d3& d)  (false = nothing to trace),
+//                                void retire(int item, int id, double t).
+template <bool ANY, class Job>
+__device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int total, unsigned long long* work, int thresh)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int batch_next = 0, batch_end = 0;
+    bool more = total > 0;
+    int item = -1;
+    int pend = 0;
+    Trav T;
+    T.node = kDone; T.sp = 0; T.id_best = -1; T.t_best = 0; T.tmax = 0;
+    int stack[kStackDepth];
+
+    for (;;) {
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {  // a batch may run out mid-way: second pass opens the next one
+            unsigned idle = __ballot_sync(FULL, item < 0);
+            if (!idle || !more) break;
+            if (batch_next >= batch_end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(work, (unsigned long long)kFetchBatch);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= (unsigned long long)total) { more = false; break; }
+                batch_next = (int)base;
+                batch_end = min((int)base + kFetchBatch, total);
+            }
+            if (item < 0) {
+                int cand = batch_next + __popc(idle & lt_mask);
+                if (cand < batch_end) {
+                    item = cand;
+                    d3 o, d;
+                    pend = 0;
+                    if (job.load(item, o, d)) trav_init(T, B, o, d);
+                    else { T.node = kDone; T.id_best = -1; T.sp = 0; }
+                }
+            }
+            batch_next = min(batch_next + __popc(idle), batch_end);
+        }
+        const unsigned live = __ballot_sync(FULL, item >= 0);
+        if (!live) break;
+        const int need = min(thresh, __popc(live));
+
+        for (;;) {
+            while (T.node >= 0) trav_internal(T, B, stack, pend);
+            // the lane now holds up to two leaves: T.node (if not kDone) and pend
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+                int leaf = (j == 0) ? (T.node != kDone ? T.node : 0) : pend;
+                if (leaf < 0) {
+                    bool hit = leaf_test<ANY>(T, B, leaf);
+                    if (ANY && hit) { T.sp = 0; pend = 0; T.node = kDone; }
+                }
+            }
+            pend = 0;
+            if (T.node != kDone) T.node = T.sp ? stack[--T.sp] : kDone;
+            unsigned fin = __ballot_sync(FULL, item >= 0 && T.node == kDone);
+            if (__popc(fin) >= need) break;
+        }
+        if (item >= 0 && T.node == kDone) {
+            job.retire(item, T.id_best, T.t_best);
+            item = -1;
+        }
+    }
+}
+
+// ---- Q1 ------------------------------------------------------------------------------------------
+struct EntryJob {
+    const double* __restrict__ origin;
+    const double* __restrict__ dir;
+    double* __restrict__ out_ori;
+    double* __restrict__ out_dir;
+    uint8_t* __restrict__ mask3;
+    uint8_t* __restrict__ hit1;
+    int4* __restrict__ L;
+    int* __restrict__ countL;
+    __device__ __forceinline__ bool load(int i, d3& o, d3& d) const
+    {
+        o = ld3(origin + 3 * (int64_t)i);
+        d = ld3(dir + 3 * (int64_t)i);
+        return true;
+    }
+    __device__ __forceinline__ void retire(int i, int id, double) const
+    {
+        if (hit1) hit1[i] = id >= 0 ? 1 : 0;
+        if (id < 0) write_invalid(out_ori, out_dir, mask3, i);
+        int slot = warp_append<>(countL, id >= 0);
+        if (slot >= 0) L[slot] = make_int4(i, id, -1, 0);
+    }
+};
+
+__global__ void __launch_bounds__(128) wf_q1_kernel(BvhView B, EntryJob job, int N, unsigned long long* work, int thresh)
+{
+    persistent_query<false>(B, job, N, work, thresh);
+}
+
+// ---- R1: refraction at the entry hit, dense over L ------------------------------------------------
+__global__ void __launch_bounds__(128) wf_r1_kernel(BvhView B, const double* __restrict__ V64,
+                                                    const double* __restrict__ origin, const double* __restrict__ dir,
+                                                    double ext_ior, double int_ior, double* __restrict__ out_ori,
+                                                    double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
+                                                    int4* __restrict__ L, const int* __restrict__ countL)
+{
+    const int n = *countL;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        int4 e = L[k];
+        const int64_t i = e.x;
+        HitRec h;
+        d3 a0, a1, a2, o1, d1;
+        load_tri64(B, V64, e.y, a0, a1, a2);
+        hit_forward(h, ld3(origin + 3 * i), ld3(dir + 3 * i), a0, a1, a2, ext_ior, int_ior, o1, d1);
+        if (h.tir) {
+            write_invalid(out_ori, out_dir, mask3, i);
+            L[k].w = 1;  // dead
+        } else {
+            st3(out_ori + 3 * i, o1);  // parked: read back by Q2 and R2
+            st3(out_dir + 3 * i, d1);
+        }
+    }
+}
+
+// ---- Q2 ------------------------------------------------------------------------------------------
+struct ExitJob {
+    const double* __restrict__ out_ori;
+    const double* __restrict__ out_dir;
+    int4* __restrict__ L;
+    __device__ __forceinline__ bool load(int k, d3& o, d3& d) const
+    {
+        int4 e = L[k];
+        if (e.w) return false;
+        o = ld3(out_ori + 3 * (int64_t)e.x);
+        d = ld3(out_dir + 3 * (int64_t)e.x);
+        return true;
+    }
+    __device__ __forceinline__ void retire(int k, int id, double) const { L[k].z = id; }
+};
+
+__global__ void __launch_bounds__(128) wf_q2_kernel(BvhView B, ExitJob job, const int* __restrict__ countL,
+                                                    unsigned long long* work, int thresh)
+{
+    persistent_query<false>(B, job, *countL, work, thresh);
+}
+
+// ---- R2: refraction at the exit hit, dense over L; survivors -> M ---------------------------------
+__global__ void __launch_bounds__(128) wf_r2_kernel(BvhView B, const double* __restrict__ V64, double ext_ior,
+                                                    double int_ior, double* __restrict__ out_ori,
+                                                    double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
+                                                    const int4* __restrict__ L, const int* __restrict__ countL,
+                                                    int4* __restrict__ M, int* __restrict__ countM)
+{
+    const int n = *countL;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int4 e = L[k];
+        const int64_t i = e.x;
+        bool alive = false;
+        if (!e.w) {  // dead entries were zeroed by R1
+            if (e.z >= 0) {
+                HitRec h;
+                d3 a0, a1, a2, o2, d2;
+                load_tri64(B, V64, e.z, a0, a1, a2);
+                hit_forward(h, ld3(out_ori + 3 * i), ld3(out_dir + 3 * i), a0, a1, a2, ext_ior, int_ior, o2, d2);
+                alive = !h.tir;
+                if (alive) {
+                    st3(out_ori + 3 * i, o2);  // the exit ray, at its final place unless Q3 finds an occluder
+                    st3(out_dir + 3 * i, d2);
+                }
+            }
+            if (!alive) write_invalid(out_ori, out_dir, mask3, i);
+        }
+        int slot = warp_append<>(countM, alive);
+        if (slot >= 0) M[slot] = e;
+    }
+}
+
+// ---- Q3 ------------------------------------------------------------------------------------------
+struct OcclusionJob {
+    double* __restrict__ out_ori;
+    double* __restrict__ out_dir;
+    uint8_t* __restrict__ mask3;
+    const int4* __restrict__ M;
+    int4* __restrict__ rec;
+    int* __restrict__ rec_count;
+    __device__ __forceinline__ bool load(int k, d3& o, d3& d) const
+    {
+        const int64_t i = M[k].x;
+        o = ld3(out_ori + 3 * i);
+        d = ld3(out_dir + 3 * i);
+        return true;
+    }
+    __device__ __forceinline__ void retire(int k, int id, double) const
+    {
+        const int4 e = M[k];
+        const int64_t i = e.x;
+        const bool valid = id < 0;
+        if (valid) { mask3[3 * i] = 1; mask3[3 * i + 1] = 1; mask3[3 * i + 2] = 1; }
+        else write_invalid(out_ori, out_dir, mask3, i);
+        if (rec) {
+            int slot = warp_append<>(rec_count, valid);
+            if (slot >= 0) rec[slot] = e;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(128) wf_q3_kernel(BvhView B, OcclusionJob job, const int* __restrict__ countM,
+                                                    unsigned long long* work, int thresh)
+{
+    persistent_query<true>(B, job, *countM, work, thresh);
+}
+
+}  // namespace drt

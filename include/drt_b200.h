@@ -93,25 +93,27 @@ DRT_API int drt_closest_hit(const drt_bvh* bvh, const float* ray6, int64_t N, fl
  *   ext_ior/int_ior  DiffRender.py:21 (1.00029) / optim.py:178
  *   out_ori,out_dir  float64[N,3]; zeros where the ray is not a valid two-bounce path
  *   mask3          uint8[N,3] (torch.bool layout), all three columns equal (DiffRender.py:423,431)
- *   rec_tri1/2     int32[N] hit records for drt_trace_bwd: triangle ids of hit 1 / hit 2, -1 where
- *                  the path is invalid.  May be NULL (inference only).
+ *   rec, rec_count hit records for drt_trace_bwd, COMPACT: one int32[4] = (ray index, triangle of
+ *                  hit 1, triangle of hit 2, 0) per VALID path, in completion order; rec must hold
+ *                  4*N int32 (16-byte aligned), rec_count is one device int32 that the call resets
+ *                  and the kernel increments.  Both may be NULL (inference only).
  *   hit1           optional uint8[N]: 1 where the primary ray hits anything = Scene.render_mask
  *                  (DiffRender.py:434-438) as a by-product.  May be NULL.
  */
 DRT_API int drt_trace_fwd(const drt_bvh* bvh, const double* V64, const double* origin, const double* dir, int64_t N,
                   double ext_ior, double int_ior, double* out_ori, double* out_dir, uint8_t* mask3,
-                  int32_t* rec_tri1, int32_t* rec_tri2, uint8_t* hit1, void* stream);
+                  int32_t* rec, int32_t* rec_count, uint8_t* hit1, void* stream);
 
 /*
  * Replaces loss.backward() through the autograd graph of the chain above (optim.py:210): replays
- * the cached hit records, evaluates the analytic Jacobian of (out_ori, out_dir) w.r.t. the six
+ * the compact hit records written by drt_trace_fwd (one thread per VALID path), evaluates the analytic Jacobian of (out_ori, out_dir) w.r.t. the six
  * hit-triangle vertices in float64 and scatter-adds into grad_V.
  *   g_out_ori      float64[N,3] upstream gradient of out_ori, or NULL (= zeros; optim.py:100)
  *   g_out_dir      float64[N,3] upstream gradient of out_dir
  *   grad_V         float64[nV,3], ACCUMULATED into (caller zeroes) -- index_put_(accumulate=True)
  */
 DRT_API int drt_trace_bwd(const drt_bvh* bvh, const double* V64, const double* origin, const double* dir, int64_t N,
-                  double ext_ior, double int_ior, const int32_t* rec_tri1, const int32_t* rec_tri2,
+                  double ext_ior, double int_ior, const int32_t* rec, const int32_t* rec_count,
                   const double* g_out_ori, const double* g_out_dir, double* grad_V, void* stream);
 
 /*
