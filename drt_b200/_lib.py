@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "_C", "libdrt_b200.so")
+# DRT_B200_LIB: developer override used to A/B kernel variants built with different -D flags
+SO_PATH = os.environ.get("DRT_B200_LIB") or os.path.join(_HERE, "_C", "libdrt_b200.so")
 
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 

@@ -4,35 +4,39 @@
 // optix_extend.cpp:61-67: setTriangles + update(RTP_MODEL_HINT_ASYNC)).
 //
 // Pipeline (all on the caller's stream, no host sync):
-//   1 bounds   : per-triangle AABB centroid -> scene centroid bounds (warp shuffle + ordered-uint atomics)
+//   1 bounds   : per-triangle AABB centroid -> scene centroid bounds + largest |coordinate|
+//                (warp shuffle + ordered-uint atomics)
 //   2 morton   : 63-bit Morton code (21 bits/axis) of the normalised centroid
-//   3 sort     : LSD radix sort of (code, triangle id) pairs          (radix_sort.cuh)
+//   3 sort     : LSD radix sort of (code, triangle id) pairs
 //   4 topology : Karras 2012 -- one thread per internal node finds its key range and split
 //   5 fit      : bottom-up AABB union with atomic arrival counters
-//   6 emit     : traversal layout -- 64-B nodes holding BOTH children's boxes, 48-B triangle records
-//                in Morton order (float32 vertices + original id)
-// Refit = steps 5-6 only (topology kept).
+//   6 emit     : traversal layout (below)
+// Refit = steps 5 and 6 only (topology kept).
+// (A 4-wide collapse of this tree was built and measured on B200: +40 % executed instructions and
+//  35 % slower than the binary layout on the benchmark meshes -- see DESIGN.md -- so it is not kept.)
 #pragma once
 #include "common.cuh"
 
 namespace drt {
 
 // ---- traversal layout ---------------------------------------------------------------------------
-// node i = 4 x float4:
-//   q0 = (c0.lo.x, c0.lo.y, c0.lo.z, c0.hi.x)
-//   q1 = (c0.hi.y, c0.hi.z, c1.lo.x, c1.lo.y)
-//   q2 = (c1.lo.z, c1.hi.x, c1.hi.y, c1.hi.z)
-//   q3 = (child0, child1, -, -) as int bits; child >= 0: internal node index, child < 0: ~slot of a
-//        triangle record (1 triangle per leaf)
-// triangle record s = 3 x float4:
-//   r0 = (v0.x, v0.y, v0.z, v1.x)  r1 = (v1.y, v1.z, v2.x, v2.y)  r2 = (v2.z, id bits, -, -)
+// Binary node, 64 B = 4 x float4, holding BOTH children's boxes plane-major so that one FFMA per
+// plane evaluates a slab:
+//   n0 = (c0.lo.x, c0.hi.x, c1.lo.x, c1.hi.x)   n1 = same for y   n2 = same for z
+//   n3 = (link0, link1, -, -) int bits: >= 0 node index, < 0: ~slot of a triangle record (1 per leaf)
+// Every box is inflated by pmax * 2^-17 (pmax = largest |coordinate| of the mesh), which absorbs the
+// rounding of the FMA-form slab test for ray origins up to 64 * pmax away (trace.cuh: node_step).
+// Triangle record, 80 B = 5 x double2, float64 so that the exact hit test needs no conversions:
+//   a.x a.y | a.z e1.x | e1.y e1.z | e2.x e2.y | e2.z id   (a = vertex 0, e1 = v1-v0, e2 = v2-v0, all
+//   computed in float64 from the float32 vertices, i.e. exactly what the query-stage test uses)
 constexpr int kNodeQuads = 4;
-constexpr int kTriQuads = 3;
+constexpr int kTriD2 = 5;
 
 struct BvhView {
     const float4* nodes;
-    const float4* tris;
-    const int32_t* F;  // [nF,3] original faces
+    const double2* tris;
+    const int32_t* F;      // [nF,3] original faces
+    const unsigned* scene; // scene[7] = float bits of pmax
     int nTris;
 };
 
@@ -66,18 +70,25 @@ __global__ void cast_vertices_kernel(const double* __restrict__ V64, float* __re
     if (i < n3) V32[i] = __double2float_rn(V64[i]);
 }
 
-// scene[0..2] = enc(min centroid), scene[3..5] = enc(max centroid); caller presets to 0xffffffff / 0
+// scene[0..2] = enc(min centroid), scene[3..5] = enc(max centroid), scene[7] = bits of max |coordinate|;
+// caller presets to 0xffffffff / 0 / 0
 __global__ void centroid_bounds_kernel(const int32_t* __restrict__ F, const float* __restrict__ V, int nF,
                                        unsigned* __restrict__ scene)
 {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     float c[3] = {INFINITY, INFINITY, INFINITY}, C[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float amax = 0.f;
     if (f < nF) {
         float lo[3], hi[3];
         tri_box(F, V, f, lo, hi);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) c[k] = C[k] = 0.5f * lo[k] + 0.5f * hi[k];
+        for (int k = 0; k < 3; ++k) {
+            c[k] = C[k] = 0.5f * lo[k] + 0.5f * hi[k];
+            amax = fmaxf(amax, fmaxf(fabsf(lo[k]), fabsf(hi[k])));
+        }
     }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
 #pragma unroll
@@ -92,6 +103,7 @@ __global__ void centroid_bounds_kernel(const int32_t* __restrict__ F, const floa
             atomicMin(&scene[k], enc_f32(c[k]));
             atomicMax(&scene[3 + k], enc_f32(C[k]));
         }
+        atomicMax(&scene[7], __float_as_uint(amax));  // non-negative floats order like their bit patterns
     }
 }
 
@@ -195,16 +207,23 @@ __global__ void fit_kernel(const int32_t* __restrict__ F, const float* __restric
     }
 }
 
+__device__ __forceinline__ float4 planes(float lo0, float hi0, float lo1, float hi1, float infl)
+{
+    return make_float4(__fadd_rd(lo0, -infl), __fadd_ru(hi0, infl), __fadd_rd(lo1, -infl), __fadd_ru(hi1, infl));
+}
+
 __global__ void emit_nodes_kernel(int n, const int2* __restrict__ children, const float4* __restrict__ blo,
-                                  const float4* __restrict__ bhi, float4* __restrict__ nodes)
+                                  const float4* __restrict__ bhi, const unsigned* __restrict__ scene,
+                                  float4* __restrict__ nodes)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float infl = __uint_as_float(scene[7]) * 7.62939453125e-06f;  // pmax * 2^-17
     if (n == 1) {
         if (i == 0) {  // single triangle: child 0 = the leaf, child 1 = an empty box that is never hit
             float4 l = blo[0], h = bhi[0];
-            nodes[0] = make_float4(l.x, l.y, l.z, h.x);
-            nodes[1] = make_float4(h.y, h.z, INFINITY, INFINITY);
-            nodes[2] = make_float4(INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            nodes[0] = planes(l.x, h.x, INFINITY, -INFINITY, infl);
+            nodes[1] = planes(l.y, h.y, INFINITY, -INFINITY, infl);
+            nodes[2] = planes(l.z, h.z, INFINITY, -INFINITY, infl);
             nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.f, 0.f);
         }
         return;
@@ -214,24 +233,31 @@ __global__ void emit_nodes_kernel(int n, const int2* __restrict__ children, cons
     float4 l0 = blo[ch.x], h0 = bhi[ch.x], l1 = blo[ch.y], h1 = bhi[ch.y];
     int c0 = ch.x >= n - 1 ? ~(ch.x - (n - 1)) : ch.x;
     int c1 = ch.y >= n - 1 ? ~(ch.y - (n - 1)) : ch.y;
-    nodes[4 * (size_t)i + 0] = make_float4(l0.x, l0.y, l0.z, h0.x);
-    nodes[4 * (size_t)i + 1] = make_float4(h0.y, h0.z, l1.x, l1.y);
-    nodes[4 * (size_t)i + 2] = make_float4(l1.z, h1.x, h1.y, h1.z);
-    nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(c0), __int_as_float(c1), 0.f, 0.f);
+    float4* node = nodes + (size_t)i * kNodeQuads;
+    node[0] = planes(l0.x, h0.x, l1.x, h1.x, infl);
+    node[1] = planes(l0.y, h0.y, l1.y, h1.y, infl);
+    node[2] = planes(l0.z, h0.z, l1.z, h1.z, infl);
+    node[3] = make_float4(__int_as_float(c0), __int_as_float(c1), 0.f, 0.f);
 }
 
 __global__ void emit_tris_kernel(const int32_t* __restrict__ F, const float* __restrict__ V,
-                                 const uint32_t* __restrict__ vals, int n, float4* __restrict__ tris)
+                                 const uint32_t* __restrict__ vals, int n, double2* __restrict__ tris)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     int f = (int)vals[k];
-    const float* a = &V[3 * (size_t)F[3 * f]];
-    const float* b = &V[3 * (size_t)F[3 * f + 1]];
-    const float* c = &V[3 * (size_t)F[3 * f + 2]];
-    tris[3 * (size_t)k + 0] = make_float4(a[0], a[1], a[2], b[0]);
-    tris[3 * (size_t)k + 1] = make_float4(b[1], b[2], c[0], c[1]);
-    tris[3 * (size_t)k + 2] = make_float4(c[2], __int_as_float(f), 0.f, 0.f);
+    const float* pa = &V[3 * (size_t)F[3 * f]];
+    const float* pb = &V[3 * (size_t)F[3 * f + 1]];
+    const float* pc = &V[3 * (size_t)F[3 * f + 2]];
+    d3 a = mk3((double)pa[0], (double)pa[1], (double)pa[2]);
+    d3 e1 = mk3((double)pb[0], (double)pb[1], (double)pb[2]) - a;
+    d3 e2 = mk3((double)pc[0], (double)pc[1], (double)pc[2]) - a;
+    double2* t = tris + (size_t)k * kTriD2;
+    t[0] = make_double2(a.x, a.y);
+    t[1] = make_double2(a.z, e1.x);
+    t[2] = make_double2(e1.y, e1.z);
+    t[3] = make_double2(e2.x, e2.y);
+    t[4] = make_double2(e2.z, __longlong_as_double((long long)f));
 }
 
 // faces must index inside [0,nV): checked on the device, result read lazily by drt_bvh_info

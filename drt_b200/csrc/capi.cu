@@ -51,16 +51,18 @@ constexpr int kWorkSlots = 64;
 // tuning knobs (read once): DRT_FWD_KERNEL = wavefront (default) | simple | prof ; DRT_FWD_THRESH = 1..32
 struct Tuning {
     bool simple_fwd = false;
-    bool prof = false;
-    int thresh = 16;
+    int thresh = 32;
+    int minb = 8;
     Tuning()
     {
         const char* k = getenv("DRT_FWD_KERNEL");
         if (k && !strcmp(k, "simple")) simple_fwd = true;
-        if (k && !strcmp(k, "prof")) simple_fwd = prof = true;
 
         const char* t = getenv("DRT_FWD_THRESH");
         if (t && atoi(t) >= 1 && atoi(t) <= 32) thresh = atoi(t);
+        const char* m = getenv("DRT_Q_MINB");
+        if (m) minb = atoi(m);
+        if (minb != 4 && minb != 6 && minb != 8 && minb != 10) minb = 8;
     }
 };
 const Tuning& tuning()
@@ -98,9 +100,9 @@ struct drt_bvh {
     uint32_t* sorted_vals = nullptr;             // points into vals (which half holds the sorted ids)
     // traversal data
     float4* nodes = nullptr;   size_t capN = 0;
-    float4* tris = nullptr;    size_t capT = 0;
+    double2* tris = nullptr;   size_t capT = 0;
 
-    BvhView view() const { return BvhView{nodes, tris, F, nF}; }
+    BvhView view() const { return BvhView{nodes, tris, F, scene, nF}; }
 };
 
 namespace {
@@ -133,7 +135,7 @@ __global__ void copy_faces_kernel(const int32_t* __restrict__ in, int32_t* __res
 __global__ void init_scene_kernel(unsigned* scene, bool reset_bad)
 {
     if (threadIdx.x < 3) scene[threadIdx.x] = 0xffffffffu;
-    else if (threadIdx.x < 6) scene[threadIdx.x] = 0u;
+    else if (threadIdx.x < 6 || threadIdx.x == 7) scene[threadIdx.x] = 0u;
     else if (threadIdx.x == 6 && reset_bad) scene[6] = 0u;
 }
 
@@ -144,7 +146,7 @@ int fit_and_emit(drt_bvh* b, cudaStream_t st)
     if (n > 1) CU(cudaMemsetAsync(b->flags, 0, sizeof(int) * (size_t)(n - 1), st));
     fit_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_vals, n, b->children, b->parent, b->blo, b->bhi,
                                                     b->flags); ++g_launches;
-    emit_nodes_kernel<<<blocks_for(n > 1 ? n - 1 : 1, 256), 256, 0, st>>>(n, b->children, b->blo, b->bhi, b->nodes); ++g_launches;
+    emit_nodes_kernel<<<blocks_for(n > 1 ? n - 1 : 1, 256), 256, 0, st>>>(n, b->children, b->blo, b->bhi, b->scene, b->nodes); ++g_launches;
     emit_tris_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_vals, n, b->tris); ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
@@ -165,7 +167,7 @@ int build_tree(drt_bvh* b, cudaStream_t st)
     if ((rc = ensure(b->bhi, b->capBh, 2 * (size_t)n))) return rc;
     if ((rc = ensure(b->flags, b->capFl, (size_t)n))) return rc;
     if ((rc = ensure(b->nodes, b->capN, (size_t)kNodeQuads * (size_t)(n > 1 ? n - 1 : 1)))) return rc;
-    if ((rc = ensure(b->tris, b->capT, (size_t)kTriQuads * (size_t)n))) return rc;
+    if ((rc = ensure(b->tris, b->capT, (size_t)kTriD2 * (size_t)n))) return rc;
 
     init_scene_kernel<<<1, 32, 0, st>>>(b->scene, false); ++g_launches;
     centroid_bounds_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene); ++g_launches;
@@ -258,8 +260,7 @@ int drt_bvh_create(int device, drt_bvh** out)
     CU(cudaMalloc(&b->scene, 8 * sizeof(unsigned)));
     CU(cudaMemset(b->scene, 0, 8 * sizeof(unsigned)));
     CU(cudaMalloc(&b->work, kWorkSlots * sizeof(unsigned long long)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->fwd_blocks_per_sm, wf_q1_kernel, 128, 0));
-    if (b->fwd_blocks_per_sm < 1) b->fwd_blocks_per_sm = 1;
+
     *out = b;
     return DRT_OK;
 }
@@ -309,7 +310,7 @@ int drt_bvh_info(const drt_bvh* b, int64_t info[8])
     info[0] = b->nF; info[1] = b->nV; info[2] = b->nF > 1 ? b->nF - 1 : (b->nF == 1 ? 1 : 0);
     info[3] = b->built ? 1 : 0;
     info[4] = info[2] * (int64_t)(kNodeQuads * sizeof(float4));
-    info[5] = (int64_t)b->nF * (int64_t)(kTriQuads * sizeof(float4));
+    info[5] = (int64_t)b->nF * (int64_t)(kTriD2 * sizeof(double2));
     info[6] = b->builds; info[7] = b->refits;
     return DRT_OK;
 }
@@ -357,20 +358,8 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
     if (b->nF > 0 && !V64) return fail(DRT_ERR_INVALID, "drt_trace_fwd: V64 is null");
     if (tuning().simple_fwd) {
         int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
-        if (tuning().prof) {
-            // utilisation probe (debug): 12 counters = {warp iters, lane iters} x {internal, leaf} x 3 queries
-            CU(cudaMemsetAsync(b->work, 0, 12 * sizeof(unsigned long long), st));
-            trace_fwd_kernel<true><<<grid, 128, 0, st>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir, mask3,
-                                                         (int4*)rec, rec_count, hit1, b->work);
-            unsigned long long c[12];
-            CU(cudaMemcpyAsync(c, b->work, sizeof(c), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            for (int q = 0; q < 3; ++q)
-                fprintf(stderr, "[drt prof] Q%d internal: %llu warp-iters, %.2f lanes/iter | leaf: %llu warp-iters, %.2f lanes/iter\n", q + 1,
-                        c[4 * q], c[4 * q] ? (double)c[4 * q + 1] / c[4 * q] : 0.0, c[4 * q + 2], c[4 * q + 2] ? (double)c[4 * q + 3] / c[4 * q + 2] : 0.0);
-        } else
-            trace_fwd_kernel<false><<<grid, 128, 0, st>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir, mask3,
-                                                          (int4*)rec, rec_count, hit1, nullptr);
+        trace_fwd_kernel<<<grid, 128, 0, st>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir, mask3,
+                                               (int4*)rec, rec_count, hit1);
     } else {
         // production path: wavefront of persistent query kernels (wavefront.cuh)
         int rc;
@@ -382,16 +371,25 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
         int* countL = (int*)(ctl + 3);
         int* countM = countL + 1;
         const int thresh = tuning().thresh;
-        const int pgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * b->fwd_blocks_per_sm);
         const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
         EntryJob j1{origin, dir, out_ori, out_dir, mask3, hit1, b->listA, countL};
-        wf_q1_kernel<<<pgrid, 128, 0, st>>>(b->view(), j1, (int)N, ctl + 0, thresh);
+        const int minb = tuning().minb;
+        const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
+#define DRT_LAUNCH_Q(KERNEL, ...)                                                           \
+    do {                                                                                    \
+        if (minb == 10) KERNEL<10><<<pg, 128, 0, st>>>(__VA_ARGS__);                        \
+        else if (minb == 8) KERNEL<8><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
+        else if (minb == 6) KERNEL<6><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
+        else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
+    } while (0)
+        DRT_LAUNCH_Q(wf_q1_kernel, b->view(), j1, (int)N, ctl + 0, thresh);
         wf_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, origin, dir, ext_ior, int_ior, out_ori, out_dir, mask3, b->listA, countL);
         ExitJob j2{out_ori, out_dir, b->listA};
-        wf_q2_kernel<<<pgrid, 128, 0, st>>>(b->view(), j2, countL, ctl + 1, thresh);
+        DRT_LAUNCH_Q(wf_q2_kernel, b->view(), j2, countL, ctl + 1, thresh);
         wf_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, out_ori, out_dir, mask3, b->listA, countL, b->listB, countM);
         OcclusionJob j3{out_ori, out_dir, mask3, b->listB, (int4*)rec, rec_count};
-        wf_q3_kernel<<<pgrid, 128, 0, st>>>(b->view(), j3, countM, ctl + 2, thresh);
+        DRT_LAUNCH_Q(wf_q3_kernel, b->view(), j3, countM, ctl + 2, thresh);
+#undef DRT_LAUNCH_Q
         g_launches += 4;
     }
     ++g_launches;

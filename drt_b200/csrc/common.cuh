@@ -40,21 +40,37 @@ __device__ __forceinline__ void st3(double* __restrict__ p, d3 v) { p[0] = v.x; 
 
 // ------------------------------------------------------------------------------------------------
 // Query-stage triangle test: float64 Moller-Trumbore on float32-rounded data, closed triangle,
-// accept (float)t > 0 (DiffRender.py:391).  Same expression tree as oracle/drt_oracle.c:query_tri.
+// accept (float)t > 0 (DiffRender.py:391).  Decides exactly like oracle/drt_oracle.c:query_tri:
+// the accepted path evaluates the identical expression tree (e1 = b-a and e2 = c-a are precomputed
+// in float64 at build time with the same rounding), and the early rejections below only fire when
+// the reference expression is PROVABLY rejected too:
+//   u = fl(U*fl(1/det)) with U = tvec.pvec.  If U and det have opposite signs (|U| > 1e-150, so the
+//   product cannot underflow to -0) then u < 0; if |U| > |det|(1+2^-40) then |u| > 1 because the two
+//   roundings lose at most 2^-51 relatively.  Same for v, u+v (no cancellation when the signs agree)
+//   and the sign of t.  det == 0 gives u = +-inf or NaN in the reference: rejected.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool query_tri(d3 o, d3 d, d3 a, d3 b, d3 c, double& t_out)
+__device__ __forceinline__ bool opposite(double x, double det) { return ((x < 0.0) != (det < 0.0)) && fabs(x) > 1e-150; }
+
+__device__ __forceinline__ bool query_tri(d3 o, d3 d, d3 a, d3 e1, d3 e2, double& t_out)
 {
-    d3 e1 = b - a, e2 = c - a;
     d3 pvec = cross(d, e2);
     double det = dot(e1, pvec);
-    double inv = __ddiv_rn(1.0, det);
+    if (det == 0.0) return false;
     d3 tvec = o - a;
-    double u = mulr(dot(tvec, pvec), inv);
-    if (!(u >= 0.0 && u <= 1.0)) return false;
+    double U = dot(tvec, pvec);
+    const double lim = mulr(fabs(det), 1.0000000000009094947017729282379150390625);  // |det| (1 + 2^-40)
+    if (opposite(U, det) || fabs(U) > lim) return false;
     d3 qvec = cross(tvec, e1);
-    double v = mulr(dot(d, qvec), inv);
+    double V = dot(d, qvec);
+    if (opposite(V, det) || addr(fabs(U), fabs(V)) > lim) return false;
+    double T = dot(e2, qvec);
+    if (opposite(T, det)) return false;
+    double inv = __ddiv_rn(1.0, det);
+    double u = mulr(U, inv);
+    if (!(u >= 0.0 && u <= 1.0)) return false;
+    double v = mulr(V, inv);
     if (!(v >= 0.0 && addr(u, v) <= 1.0)) return false;
-    double t = mulr(dot(e2, qvec), inv);
+    double t = mulr(T, inv);
     if (!(__double2float_rn(t) > 0.0f)) return false;
     t_out = t;
     return true;

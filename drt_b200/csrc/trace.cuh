@@ -8,7 +8,8 @@
 
 namespace drt {
 
-constexpr int kStackDepth = 96;  // >= 63 Morton bits + index tie-break levels of a Karras tree
+constexpr int kStackDepth = 96 + 8;  // binary Karras depth <= 63 key bits + 32 index bits, + deferred leaves
+constexpr int kDone = INT_MIN;
 
 struct QRay {        // query ray = float32 cast of the chain's float64 ray (DiffRender.py:387-388)
     float ox, oy, oz, dx, dy, dz;
@@ -20,86 +21,147 @@ __device__ __forceinline__ QRay cast_ray(d3 o, d3 d)
                 __double2float_rn(d.x), __double2float_rn(d.y), __double2float_rn(d.z)};
 }
 
-// Closed-box slab test with near/far planes picked by the direction sign.  A zero direction
-// component yields +-inf (origin strictly inside / outside the slab) or NaN (origin exactly on a
-// slab plane); fmaxf/fminf drop the NaN, i.e. "no constraint", which is right for a ray running
-// inside a face plane.  (plane - o) * inv carries <= 3 half-ulps of relative error, the 2^-20
-// slack below makes the test conservative, so the exact float64 triangle test decides every hit.
-__device__ __forceinline__ bool slab(float lx, float ly, float lz, float hx, float hy, float hz, const QRay& r,
-                                     float ix, float iy, float iz, bool nx, bool ny, bool nz, float tmax, float& tnear)
+// ---------------------------------------------------------------------------------------------
+// Slab test of the child boxes of a node, FMA form:  t = plane * (1/d) - o * (1/d).
+//
+// Conservativeness (the float64 triangle test, never a box test, must decide every hit):
+//   with inv = fl(1/d), c = fl(o*inv) the FMA returns (plane - o)/d * (1+e1)(1+e3) - (o/d)(1+e1)(1+e3) e2,
+//   |e| <= 2^-24.  The last term equals moving the plane by |o| 2^-24: covered by the build-time box
+//   inflation of pmax 2^-17 for every |o| <= 64 pmax (2x margin); rays starting farther away carry
+//   the same bound as an additive slack E (ray_setup).  The relative terms are covered by the
+//   factor 1 + 2^-20 on tfar.  A direction component with |d| < 2^-100 (including 0) is given
+//   inv = +-2^100: finite, so no inf - inf, and the same error analysis holds -- the ray then
+//   passes every box whose (inflated) slab contains its origin on that axis, which is the closed-box
+//   answer for an axis-parallel ray.  Empty child slots (lo = +inf, hi = -inf) never pass.
+// ---------------------------------------------------------------------------------------------
+struct RayQ {
+    QRay r;
+    float ix, iy, iz;  // 1/d
+    float cx, cy, cz;  // o/d
+    float E;           // additive slack, 0 for origins within 64*pmax
+};
+
+__device__ __forceinline__ float safe_inv(float d)
 {
-    float t0 = fmaxf(fmaxf(fmaxf(0.f, ((nx ? hx : lx) - r.ox) * ix), ((ny ? hy : ly) - r.oy) * iy),
-                     ((nz ? hz : lz) - r.oz) * iz);
-    float t1 = fminf(fminf(fminf(tmax, ((nx ? lx : hx) - r.ox) * ix), ((ny ? ly : hy) - r.oy) * iy),
-                     ((nz ? lz : hz) - r.oz) * iz);
-    tnear = t0;
-    return t0 <= t1 * 1.00000095367431640625f;
+    return fabsf(d) < 7.888609052210118e-31f ? copysignf(1.2676506002282294e30f, d) : __fdiv_rn(1.f, d);
+}
+
+__device__ __forceinline__ RayQ ray_setup(const BvhView& B, const QRay& r)
+{
+    RayQ q;
+    q.r = r;
+    q.ix = safe_inv(r.dx); q.iy = safe_inv(r.dy); q.iz = safe_inv(r.dz);
+    q.cx = r.ox * q.ix; q.cy = r.oy * q.iy; q.cz = r.oz * q.iz;
+    const float pmax = __uint_as_float(__ldg(B.scene + 7));
+    const float far = fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz)));
+    q.E = 0.f;
+    if (!(far <= 64.f * pmax))
+        q.E = 2.384185791015625e-07f * fmaxf(fabsf(q.cx), fmaxf(fabsf(q.cy), fabsf(q.cz)));  // 2^-22 |o/d|
+    return q;
+}
+
+// one binary node: test both children, continue with the nearer hit, push the other
+__device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float tmax, int node, int* stack, int& sp)
+{
+    const float4* p = B.nodes + (size_t)node * kNodeQuads;
+    const float4 nx = __ldg(p), ny = __ldg(p + 1), nz = __ldg(p + 2);
+    const float4 nl = __ldg(p + 3);
+    // child 0: planes .x/.y, child 1: planes .z/.w
+    const float ax0 = fmaf(nx.x, q.ix, -q.cx), bx0 = fmaf(nx.y, q.ix, -q.cx), ax1 = fmaf(nx.z, q.ix, -q.cx), bx1 = fmaf(nx.w, q.ix, -q.cx);
+    const float ay0 = fmaf(ny.x, q.iy, -q.cy), by0 = fmaf(ny.y, q.iy, -q.cy), ay1 = fmaf(ny.z, q.iy, -q.cy), by1 = fmaf(ny.w, q.iy, -q.cy);
+    const float az0 = fmaf(nz.x, q.iz, -q.cz), bz0 = fmaf(nz.y, q.iz, -q.cz), az1 = fmaf(nz.z, q.iz, -q.cz), bz1 = fmaf(nz.w, q.iz, -q.cz);
+    const float n0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fmaxf(fminf(az0, bz0), 0.f));
+    const float f0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fminf(fmaxf(az0, bz0), tmax));
+    const float n1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fmaxf(fminf(az1, bz1), 0.f));
+    const float f1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fminf(fmaxf(az1, bz1), tmax));
+    const bool h0 = n0 <= fmaf(f0, 1.00000095367431640625f, q.E);
+    const bool h1 = n1 <= fmaf(f1, 1.00000095367431640625f, q.E);
+    const int c0 = __float_as_int(nl.x), c1 = __float_as_int(nl.y);
+    if (h0 && h1) {
+        const bool first0 = n0 <= n1;
+        stack[sp++] = first0 ? c1 : c0;
+        return first0 ? c0 : c1;
+    }
+    if (h0) return c0;
+    if (h1) return c1;
+    return sp ? stack[--sp] : kDone;
+}
+
+// exact test of the one triangle of a leaf; updates the closest hit (ties -> lowest id)
+__device__ __forceinline__ bool leaf_step(const BvhView& B, const QRay& r, int leaf, double& t_best, int& id_best, float& tmax)
+{
+    const double2* p = B.tris + (size_t)(~leaf) * kTriD2;
+    const double2 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
+    double t;
+    if (!query_tri(mk3((double)r.ox, (double)r.oy, (double)r.oz), mk3((double)r.dx, (double)r.dy, (double)r.dz),
+                   mk3(w0.x, w0.y, w1.x), mk3(w1.y, w2.x, w2.y), mk3(w3.x, w3.y, w4.x), t))
+        return false;
+    const int id = (int)__double_as_longlong(w4.y);
+    if (t < t_best || (t == t_best && id < id_best)) {
+        t_best = t;
+        id_best = id;
+        tmax = __double2float_ru(t);
+    }
+    return true;
+}
+
+// Leaves are DEFERRED: a lane that reaches a leaf parks it in a small per-lane queue (kept at the
+// top end of its stack array) and keeps walking internal nodes; the exact triangle tests run in
+// batches once kDefer leaves are queued or the walk is over.  Measured on B200 with test-at-once
+// traversal, a warp entered the (long, float64) leaf phase every ~1.5 node steps with ~2 of 32
+// lanes active -- every lane parked at a leaf stalls until the slowest lane reaches one.  Deferral
+// costs some closest-hit pruning (tmax is updated a few nodes later), never correctness: every leaf
+// whose box passed the test is still tested, and ties still resolve to the lowest id.
+#ifndef DRT_DEFER
+#define DRT_DEFER 4
+#endif
+constexpr int kDefer = DRT_DEFER;
+
+// walk until the stack is exhausted or kDefer leaves are queued
+__device__ __forceinline__ void walk(const BvhView& B, const RayQ& q, float tmax, int& node, int* stack, int& sp, int& nd)
+{
+    while (node != kDone && nd < kDefer) {
+        if (node >= 0) {
+            node = node_step(B, q, tmax, node, stack, sp);
+        } else {
+            stack[kStackDepth - 1 - nd] = node;
+            ++nd;
+            node = sp ? stack[--sp] : kDone;
+        }
+    }
+}
+
+// test the queued leaves; returns true as soon as ANY is satisfied
+template <bool ANY>
+__device__ __forceinline__ bool drain(const BvhView& B, const QRay& r, int* stack, int& nd, double& t_best, int& id_best,
+                                      float& tmax)
+{
+    while (nd > 0) {
+        --nd;
+        bool hit = leaf_step(B, r, stack[kStackDepth - 1 - nd], t_best, id_best, tmax);
+        if (ANY && hit) { nd = 0; return true; }
+    }
+    return false;
 }
 
 // Exact closest hit (ANY = false) or first hit found (ANY = true; only hit/no-hit is meaningful,
 // which is all the reference uses of its third query: DiffRender.py:426-427).
 // Returns triangle id (-1 on miss) and the float64 distance along the float32 ray.
-template <bool ANY, bool PROF = false>
-__device__ __forceinline__ void traverse(const BvhView& B, const QRay& r, double& t_best, int& id_best,
-                                         unsigned long long* prof = nullptr)
+template <bool ANY>
+__device__ __forceinline__ void traverse(const BvhView& B, const QRay& r, double& t_best, int& id_best)
 {
     t_best = INFINITY;
     id_best = -1;
     if (B.nTris <= 0) return;
-    const float ix = __fdiv_rn(1.f, r.dx), iy = __fdiv_rn(1.f, r.dy), iz = __fdiv_rn(1.f, r.dz);
-    const bool nx = signbit(ix), ny = signbit(iy), nz = signbit(iz);
-    const d3 o = mk3((double)r.ox, (double)r.oy, (double)r.oz);
-    const d3 d = mk3((double)r.dx, (double)r.dy, (double)r.dz);
+    const RayQ q = ray_setup(B, r);
     float tmax = INFINITY;
     int stack[kStackDepth];
-    int sp = 0;
+    int sp = 0, nd = 0;
     int node = 0;
     for (;;) {
-        while (node >= 0) {
-            if (PROF) {  // utilisation probe: warp-iterations vs lane-iterations of the internal-node loop
-                unsigned m = __activemask();
-                if ((threadIdx.x & 31) == __ffs(m) - 1) { atomicAdd(prof, 1ull); atomicAdd(prof + 1, (unsigned long long)__popc(m)); }
-            }
-            const float4* p = B.nodes + (size_t)node * kNodeQuads;
-            float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
-            float ta, tb;
-            bool ha = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, ix, iy, iz, nx, ny, nz, tmax, ta);
-            bool hb = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, ix, iy, iz, nx, ny, nz, tmax, tb);
-            int ca = __float_as_int(q3.x), cb = __float_as_int(q3.y);
-            if (ha && hb) {
-                bool a_first = ta <= tb;
-                node = a_first ? ca : cb;
-                if (sp < kStackDepth) stack[sp++] = a_first ? cb : ca;
-            } else if (ha) {
-                node = ca;
-            } else if (hb) {
-                node = cb;
-            } else {
-                if (sp == 0) return;
-                node = stack[--sp];
-            }
-        }
-        {
-            if (PROF) {
-                unsigned m = __activemask();
-                if ((threadIdx.x & 31) == __ffs(m) - 1) { atomicAdd(prof + 2, 1ull); atomicAdd(prof + 3, (unsigned long long)__popc(m)); }
-            }
-            const float4* p = B.tris + (size_t)(~node) * kTriQuads;
-            float4 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
-            double t;
-            if (query_tri(o, d, mk3((double)r0.x, (double)r0.y, (double)r0.z), mk3((double)r0.w, (double)r1.x, (double)r1.y),
-                          mk3((double)r1.z, (double)r1.w, (double)r2.x), t)) {
-                int id = __float_as_int(r2.y);
-                if (t < t_best || (t == t_best && id < id_best)) {
-                    t_best = t;
-                    id_best = id;
-                    tmax = __double2float_ru(t);
-                }
-                if (ANY) return;
-            }
-        }
-        if (sp == 0) return;
-        node = stack[--sp];
+        walk(B, q, tmax, node, stack, sp, nd);
+        if (drain<ANY>(B, r, stack, nd, t_best, id_best, tmax)) return;
+        if (node == kDone) return;
     }
 }
 
@@ -142,14 +204,12 @@ __device__ __forceinline__ void write_invalid(double* __restrict__ out_ori, doub
 // Scene.render_transparent replacement, one launch (DiffRender.py:420-432).  v1: one thread per
 // ray walks the whole path Q1 -> refract -> Q2 -> refract -> Q3.
 // ---------------------------------------------------------------------------------------------
-template <bool PROF>
 __global__ void __launch_bounds__(128) trace_fwd_kernel(BvhView B, const double* __restrict__ V64,
                                                         const double* __restrict__ origin, const double* __restrict__ dir,
                                                         int64_t N, double ext_ior, double int_ior,
                                                         double* __restrict__ out_ori, double* __restrict__ out_dir,
                                                         uint8_t* __restrict__ mask3, int4* __restrict__ rec,
-                                                        int* __restrict__ rec_count, uint8_t* __restrict__ hit1,
-                                                        unsigned long long* __restrict__ prof)
+                                                        int* __restrict__ rec_count, uint8_t* __restrict__ hit1)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         d3 o = ld3(origin + 3 * i), d = ld3(dir + 3 * i);
@@ -157,20 +217,20 @@ __global__ void __launch_bounds__(128) trace_fwd_kernel(BvhView B, const double*
         int id1, id2 = -1, id3;
         double t;
         bool valid = false;
-        traverse<false, PROF>(B, cast_ray(o, d), t, id1, prof);
+        traverse<false>(B, cast_ray(o, d), t, id1);
         if (id1 >= 0) {
             HitRec h;
             d3 a0, a1, a2, o1, d1;
             load_tri64(B, V64, id1, a0, a1, a2);
             hit_forward(h, o, d, a0, a1, a2, ext_ior, int_ior, o1, d1);
             if (!h.tir) {
-                traverse<false, PROF>(B, cast_ray(o1, d1), t, id2, prof + 4);
+                traverse<false>(B, cast_ray(o1, d1), t, id2);
                 if (id2 >= 0) {
                     d3 o2, d2;
                     load_tri64(B, V64, id2, a0, a1, a2);
                     hit_forward(h, o1, d1, a0, a1, a2, ext_ior, int_ior, o2, d2);
                     if (!h.tir) {
-                        traverse<true, PROF>(B, cast_ray(o2, d2), t, id3, prof + 8);
+                        traverse<true>(B, cast_ray(o2, d2), t, id3);
                         if (id3 < 0) {
                             valid = true;
                             oo = o2;

@@ -21,81 +21,7 @@
 
 namespace drt {
 
-constexpr int kDone = INT_MIN;
 constexpr int kFetchBatch = 64;
-
-struct Trav {
-    QRay r;
-    float ix, iy, iz;
-    bool nx, ny, nz;
-    float tmax;
-    double t_best;
-    int id_best;
-    int node;
-    int sp;
-};
-
-__device__ __forceinline__ void trav_init(Trav& T, const BvhView& B, d3 o, d3 d)
-{
-    T.r = cast_ray(o, d);
-    T.ix = __fdiv_rn(1.f, T.r.dx); T.iy = __fdiv_rn(1.f, T.r.dy); T.iz = __fdiv_rn(1.f, T.r.dz);
-    T.nx = signbit(T.ix); T.ny = signbit(T.iy); T.nz = signbit(T.iz);
-    T.tmax = INFINITY;
-    T.t_best = INFINITY;
-    T.id_best = -1;
-    T.sp = 0;
-    T.node = B.nTris > 0 ? 0 : kDone;
-}
-
-// one internal node; a leaf reached while the lane still has internal work is POSTPONED into `pend`
-// (one slot) so that the lane keeps stepping with the rest of the warp instead of parking at it
-__device__ __forceinline__ void trav_internal(Trav& T, const BvhView& B, int* stack, int& pend)
-{
-    const float4* p = B.nodes + (size_t)T.node * kNodeQuads;
-    float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
-    float ta, tb;
-    bool ha = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, T.r, T.ix, T.iy, T.iz, T.nx, T.ny, T.nz, T.tmax, ta);
-    bool hb = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, T.r, T.ix, T.iy, T.iz, T.nx, T.ny, T.nz, T.tmax, tb);
-    int ca = __float_as_int(q3.x), cb = __float_as_int(q3.y);
-    int next;
-    if (ha && hb) {
-        bool a_first = ta <= tb;
-        next = a_first ? ca : cb;
-        if (T.sp < kStackDepth) stack[T.sp++] = a_first ? cb : ca;
-    } else if (ha) {
-        next = ca;
-    } else if (hb) {
-        next = cb;
-    } else {
-        next = T.sp ? stack[--T.sp] : kDone;
-    }
-    if (next < 0 && next != kDone && pend == 0 && T.sp > 0) {
-        pend = next;
-        next = stack[--T.sp];
-    }
-    T.node = next;
-}
-
-template <bool ANY>
-__device__ __forceinline__ bool leaf_test(Trav& T, const BvhView& B, int leaf)
-{
-    const float4* p = B.tris + (size_t)(~leaf) * kTriQuads;
-    float4 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
-    const d3 o = mk3((double)T.r.ox, (double)T.r.oy, (double)T.r.oz);
-    const d3 d = mk3((double)T.r.dx, (double)T.r.dy, (double)T.r.dz);
-    double t;
-    if (query_tri(o, d, mk3((double)r0.x, (double)r0.y, (double)r0.z), mk3((double)r0.w, (double)r1.x, (double)r1.y),
-                  mk3((double)r1.z, (double)r1.w, (double)r2.x), t)) {
-        int id = __float_as_int(r2.y);
-        if (t < T.t_best || (t == T.t_best && id < T.id_best)) {
-            T.t_best = t;
-            T.id_best = id;
-            T.tmax = __double2float_ru(t);
-        }
-        return true;
-    }
-    return false;
-}
 
 template <typename Dummy = void>
 __device__ __forceinline__ int warp_append(int* __restrict__ counter, bool pred)
@@ -114,6 +40,8 @@ __device__ __forceinline__ int warp_append(int* __restrict__ counter, bool pred)
 
 // Persistent query driver.  Job: bool load(int item, d3& o, d3& d)  (false = nothing to trace),
 //                                void retire(int item, int id, double t).
+// Lanes step their traversals together; once `thresh` of the live lanes have finished, those retire
+// and are refilled from the global work counter (thresh = 32: refill only when the whole warp is done).
 template <bool ANY, class Job>
 __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int total, unsigned long long* work, int thresh)
 {
@@ -123,9 +51,10 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
     int batch_next = 0, batch_end = 0;
     bool more = total > 0;
     int item = -1;
-    int pend = 0;
-    Trav T;
-    T.node = kDone; T.sp = 0; T.id_best = -1; T.t_best = 0; T.tmax = 0;
+    RayQ q;
+    float tmax = 0.f;
+    double t_best = 0.0;
+    int id_best = -1, node = kDone, sp = 0, nd = 0;
     int stack[kStackDepth];
 
     for (;;) {
@@ -146,9 +75,11 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
                 if (cand < batch_end) {
                     item = cand;
                     d3 o, d;
-                    pend = 0;
-                    if (job.load(item, o, d)) trav_init(T, B, o, d);
-                    else { T.node = kDone; T.id_best = -1; T.sp = 0; }
+                    t_best = INFINITY; id_best = -1; sp = 0; nd = 0; tmax = INFINITY; node = kDone;
+                    if (job.load(item, o, d) && B.nTris > 0) {
+                        q = ray_setup(B, cast_ray(o, d));
+                        node = 0;
+                    }
                 }
             }
             batch_next = min(batch_next + __popc(idle), batch_end);
@@ -158,23 +89,13 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
         const int need = min(thresh, __popc(live));
 
         for (;;) {
-            while (T.node >= 0) trav_internal(T, B, stack, pend);
-            // the lane now holds up to two leaves: T.node (if not kDone) and pend
-#pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-                int leaf = (j == 0) ? (T.node != kDone ? T.node : 0) : pend;
-                if (leaf < 0) {
-                    bool hit = leaf_test<ANY>(T, B, leaf);
-                    if (ANY && hit) { T.sp = 0; pend = 0; T.node = kDone; }
-                }
-            }
-            pend = 0;
-            if (T.node != kDone) T.node = T.sp ? stack[--T.sp] : kDone;
-            unsigned fin = __ballot_sync(FULL, item >= 0 && T.node == kDone);
+            walk(B, q, tmax, node, stack, sp, nd);
+            if (drain<ANY>(B, q.r, stack, nd, t_best, id_best, tmax)) { node = kDone; sp = 0; }
+            unsigned fin = __ballot_sync(FULL, item >= 0 && node == kDone);
             if (__popc(fin) >= need) break;
         }
-        if (item >= 0 && T.node == kDone) {
-            job.retire(item, T.id_best, T.t_best);
+        if (item >= 0 && node == kDone) {
+            job.retire(item, id_best, t_best);
             item = -1;
         }
     }
@@ -205,7 +126,8 @@ struct EntryJob {
     }
 };
 
-__global__ void __launch_bounds__(128) wf_q1_kernel(BvhView B, EntryJob job, int N, unsigned long long* work, int thresh)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) wf_q1_kernel(BvhView B, EntryJob job, int N, unsigned long long* work, int thresh)
 {
     persistent_query<false>(B, job, N, work, thresh);
 }
@@ -251,7 +173,8 @@ struct ExitJob {
     __device__ __forceinline__ void retire(int k, int id, double) const { L[k].z = id; }
 };
 
-__global__ void __launch_bounds__(128) wf_q2_kernel(BvhView B, ExitJob job, const int* __restrict__ countL,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) wf_q2_kernel(BvhView B, ExitJob job, const int* __restrict__ countL,
                                                     unsigned long long* work, int thresh)
 {
     persistent_query<false>(B, job, *countL, work, thresh);
@@ -317,7 +240,8 @@ struct OcclusionJob {
     }
 };
 
-__global__ void __launch_bounds__(128) wf_q3_kernel(BvhView B, OcclusionJob job, const int* __restrict__ countM,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) wf_q3_kernel(BvhView B, OcclusionJob job, const int* __restrict__ countM,
                                                     unsigned long long* work, int thresh)
 {
     persistent_query<true>(B, job, *countM, work, thresh);
