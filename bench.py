@@ -37,7 +37,7 @@ UNIT = "rays/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C4", choices=["C2", "C3", "C4", "C5"])
@@ -129,7 +129,7 @@ class ClockSampler(threading.Thread):
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -263,6 +263,7 @@ def run_b200(args):
     launches0 = lib.drt_kernel_launches()
     sync_all()
     sampler.active = True
+    torch.cuda.profiler.start()   # cudaProfilerStart: `ncu --profile-from-start off` then sees exactly the K timed steps
     t_wall0 = time.perf_counter()
     start, end = ev(), ev()
     start.record()
@@ -274,6 +275,7 @@ def run_b200(args):
         marks[k][5].record()
     end.record()
     torch.cuda.synchronize(dev)
+    torch.cuda.profiler.stop()
     sampler.active = False
     t_wall = time.perf_counter() - t_wall0
     launches = lib.drt_kernel_launches() - launches0
@@ -374,10 +376,11 @@ def run_b200(args):
             ach = b_fwd * (n_total / world) / (t_fwd_ms * 1e-3) / 1e9
             traffic = None
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["trace_fwd"]["dram_bytes_per_launch"]
+                per_ray = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["trace_fwd"]["dram_bytes_per_ray"]
+                traffic = per_ray * (n_total / world)  # ncu --set full capture, scaled to this launch's ray count
             except Exception:
                 pass
-            roof = {"bound": "hbm", "kernel": "trace_fwd_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            roof = {"bound": "hbm", "kernel": "fused forward = wf_q1+wf_r1+wf_q2+wf_r2+wf_q3 (one drt_trace_fwd call)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src, "bytes_per_ray_fwd": b_fwd, "bytes_per_ray_total": b_tot,
                     "kernel_ms": t_fwd_ms, "rays_per_launch": n_total // world,
                     "step_frac": (b_tot * (n_total / world) / ((t_fwd_ms + t_bwd_ms) * 1e-3) / 1e9) / peak,

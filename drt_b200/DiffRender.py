@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib, trimesh_lite
+from . import _lib, silhouette, trimesh_lite
 from . import optix  # the plugin module the reference JIT-builds (DiffRender.py:5-6)
 
 debug = False
@@ -163,3 +163,27 @@ class Scene:
     def render_mask(self, origin, ray_dir):
         _, hitted = self.optix_intersect(Ray(origin, ray_dir))
         return hitted.to(Float)
+
+    # ---- silhouette / smoothness side of the Scene contract -------------
+    def _edges(self):
+        if not self._edges_ready:  # DiffRender.py:338-355, built lazily (only vh_loss / sm_loss need it)
+            self.Edges, self.E2F, self._mean_len = silhouette.build_edge_tables(self.mesh, self.faces, self._dev)
+            self._edges_ready = True
+        return self.Edges, self.E2F
+
+    @property
+    def mean_len(self):  # optim.py:129
+        self._edges()
+        return self._mean_len
+
+    def dihedral_angle(self):  # DiffRender.py:440-443 (cosine per edge; optim.py:85)
+        _, E2F = self._edges()
+        return silhouette.dihedral_cos(self.vertices, E2F)
+
+    def silhouette_edge(self, origin):  # DiffRender.py:445-457
+        Edges, E2F = self._edges()
+        return silhouette.silhouette_edges(self.vertices, Edges, E2F, origin)
+
+    def primary_visibility(self, silhouette_edge, camera_M, origin, detach_depth=False):  # DiffRender.py:459-479
+        return silhouette.primary_visibility(self.vertices, silhouette_edge, camera_M, origin, self.optix_intersect, Ray,
+                                             resy, resx, detach_depth)

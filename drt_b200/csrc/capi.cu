@@ -47,16 +47,19 @@ int ensure(T*& p, size_t& cap, size_t need)
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
 constexpr int kWorkSlots = 64;
+constexpr int64_t kSimpleMaxRays = 1 << 20;
 
-// tuning knobs (read once): DRT_FWD_KERNEL = wavefront (default) | simple | prof ; DRT_FWD_THRESH = 1..32
+// tuning knobs (read once): DRT_FWD_KERNEL = auto (default: by batch size) | wavefront | simple ; DRT_FWD_THRESH = 1..32
 struct Tuning {
     bool simple_fwd = false;
+    bool force_wavefront = false;
     int thresh = 32;
     int minb = 8;
     Tuning()
     {
         const char* k = getenv("DRT_FWD_KERNEL");
         if (k && !strcmp(k, "simple")) simple_fwd = true;
+        if (k && !strcmp(k, "wavefront")) force_wavefront = true;
 
         const char* t = getenv("DRT_FWD_THRESH");
         if (t && atoi(t) >= 1 && atoi(t) <= 32) thresh = atoi(t);
@@ -356,7 +359,8 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
     if (N == 0) return DRT_OK;
     if (!origin || !dir || !out_ori || !out_dir || !mask3) return fail(DRT_ERR_INVALID, "drt_trace_fwd: null buffer");
     if (b->nF > 0 && !V64) return fail(DRT_ERR_INVALID, "drt_trace_fwd: V64 is null");
-    if (tuning().simple_fwd) {
+    // small batches: the five-launch wavefront has ~0.1 ms of fixed cost, the one-launch megakernel wins below ~1 M rays
+    if (tuning().simple_fwd || (!tuning().force_wavefront && N <= kSimpleMaxRays)) {
         int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
         trace_fwd_kernel<<<grid, 128, 0, st>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir, mask3,
                                                (int4*)rec, rec_count, hit1);

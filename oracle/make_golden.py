@@ -91,6 +91,34 @@ def chain_case(case, v, f, o, d, int_ior, seed, cam=None):
     print(f"{case}: {len(o)} rays, {len(idx)} valid, |grad_V|max {np.abs(r['grad_V']).max():.3g}")
 
 
+def silhouette_case():
+    """N1: the reference's silhouette_edge + primary_visibility + primary_edge_sample (DiffRender.py:445-479,
+    189-267) on hand_vh, with edge tables from drt_b200.trimesh_lite (trimesh itself is absent) and the
+    brute-force stand-in intersector."""
+    from drt_b200 import silhouette, trimesh_lite
+    R = ref_harness.load_reference()
+    v, f = plyio.read_ply(os.path.join(ref_harness.REF_ROOT, "data", "hand_vh.ply"))
+    s = ref_harness.make_scene(v, f, INT_IOR)
+    mesh = trimesh_lite.TriMesh(v, f)
+    s.Edges, s.E2F, _ = silhouette.build_edge_tables(mesh, s.faces, "cpu")
+    resy, resx = 240, 320
+    R.resy, R.resx = resy, resx
+    cams = views.turntable_cameras(v, resy, resx, 72)
+    Rm, K, R_inv, K_inv = (torch.tensor(m) for m in cams[11])
+    origin = R_inv[:3, 3].clone()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sil = s.silhouette_edge(origin)
+        index, output = s.primary_visibility(sil, (Rm, K, R_inv, K_inv), origin, detach_depth=True)
+        w = torch.tensor(np.random.default_rng(9).standard_normal(len(output)), dtype=output.dtype)
+        (output * w).sum().backward()
+        dih = R.dot(*R.edge_face_norm(s.vertices.detach(), s.E2F)).numpy()
+    np.savez_compressed(os.path.join(GOLD, "silhouette_hand_vh.npz"), view=11, res=np.array([resy, resx]),
+                        sil_edges=sil.numpy(), index=index.numpy(), output=output.detach().numpy(), weights=w.numpy(),
+                        grad_V=s.vertices.grad.numpy(), dihedral_cos=dih)
+    print(f"silhouette: {len(sil)} silhouette edges, {len(index)} samples in view, |grad|max {s.vertices.grad.abs().max():.3g}")
+
+
 def view_rays(v, resy, resx, k, n_views=72):
     cams = views.turntable_cameras(v, resy, resx, n_views)
     _, _, R_inv, K_inv = cams[k]
@@ -103,6 +131,7 @@ def main():
         sys.exit("reference tree not present; golden vectors can only be regenerated in the build container")
     save_meshes()
     kat_functions()
+    silhouette_case()
     # App. B tetrahedron (5 rays, one of them a miss)
     v, f = meshgen.tetrahedron()
     o = np.array([(0.6, 0.7, 9), (0.9, 0.5, 9), (0.4, 1.1, 9), (1.2, 0.3, 9), (3.9, 3.9, 9)], float)

@@ -1,0 +1,95 @@
+"""Turns ncu outputs in gpurun_out/ into the tracked summaries under profiles/.
+
+    python tools/summarize_profiles.py <round tag> [launches.csv] [prof.ncu-rep]
+
+Writes profiles/<tag>_launches.md (per-kernel share of a bench step, from the gpu__time_duration pass),
+profiles/<tag>_ncu_full.md (key metrics of the --set full capture) and refreshes profiles/ncu_summary.json
+(dram bytes per launch of the dominant kernels, read by bench.py for roofline.traffic)."""
+import csv, io, json, os, subprocess, sys
+from collections import OrderedDict, defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+launches = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "launches.csv")
+rep = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "prof_step.ncu-rep")
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+
+
+def short(name):
+    n = name.split("(")[0]
+    for p in ("void ", "drt::", "at::native::", "cub::CUB_300001_SM_1000::", "cub::"):
+        n = n.replace(p, "")
+    return n[:70]
+
+
+if os.path.exists(launches):
+    lines = [l for l in open(launches) if not l.startswith("==")]
+    rows = list(csv.DictReader(io.StringIO("".join(lines))))
+    per = defaultdict(lambda: [0, 0.0])
+    order = []
+    for r in rows:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        k = short(r["Kernel Name"])
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r.get("Metric Unit", "ns")
+        v_us = v / 1e3 if u in ("ns", "nsecond") else (v if u in ("us", "usecond") else v * 1e3)
+        if k not in per:
+            order.append(k)
+        per[k][0] += 1
+        per[k][1] += v_us
+    tot = sum(v[1] for v in per.values())
+    with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
+        f.write(f"# {tag}: per-kernel device time, `ncu --metrics gpu__time_duration.sum --clock-control none` over\n"
+                "`python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline` (C4, 72 views; setup + 3 steps).\n"
+                "Times are cold-cache and serialised: compare SHARES, not absolutes.\n\n"
+                "| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
+        for k in sorted(per, key=lambda k: -per[k][1]):
+            f.write(f"| `{k}` | {per[k][0]} | {per[k][1]:.1f} | {100 * per[k][1] / tot:.1f} % |\n")
+    print("wrote launches summary:", len(per), "kernels, total", round(tot / 1e3, 2), "ms")
+
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    keys = OrderedDict([
+        ("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM % of peak"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM % of peak"),
+        ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+        ("launch__registers_per_thread", "registers"), ("smsp__inst_executed.sum", "warp instructions"),
+        ("smsp__thread_inst_executed_per_inst_executed.ratio", "active lanes / instruction"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+        ("launch__grid_size", "grid"), ("launch__block_size", "block")])
+    summ = {}
+    with open(os.path.join(out_dir, f"{tag}_ncu_full.md"), "w") as f:
+        f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` of one bench step\n"
+                "(`python bench.py --steps 1 --warmup 1 --views 8`, C4 mesh, 8 views = 5 529 600 rays per launch).\n\n")
+        for r in rows[2:]:
+            name = short(r[hdr.index("Kernel Name")])
+            f.write(f"## `{name}`\n\n| metric | value |\n|---|---:|\n")
+            d = {}
+            for k, lab in keys.items():
+                if k in hdr:
+                    i = hdr.index(k)
+                    f.write(f"| {lab} (`{k}`) | {r[i]} {units[i]} |\n")
+                    d[k] = (r[i], units[i])
+            f.write("\n")
+
+            def to_bytes(v, u):
+                v = float(v.replace(",", ""))
+                return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            if "dram__bytes_read.sum" in d:
+                summ[name] = {"dram_bytes_per_launch": to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"]),
+                              "duration": " ".join(d["gpu__time_duration.sum"]), "rays_per_launch": 5529600}
+    js = os.path.join(out_dir, "ncu_summary.json")
+    allj = json.load(open(js)) if os.path.exists(js) else {}
+    allj[tag] = summ
+    # bench.py reads the forward group: sum of the five wavefront launches, scaled per ray
+    fwd = [v for k, v in summ.items() if k.startswith("wf_")]
+    if fwd:
+        allj["trace_fwd"] = {"dram_bytes_per_ray": sum(v["dram_bytes_per_launch"] for v in fwd) / 5529600, "from": tag}
+    json.dump(allj, open(js, "w"), indent=1)
+    print("wrote ncu full summary:", list(summ))
