@@ -42,7 +42,8 @@ if os.path.exists(launches):
     tot = sum(v[1] for v in per.values())
     with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
         f.write(f"# {tag}: per-kernel device time, `ncu --metrics gpu__time_duration.sum --clock-control none` over\n"
-                "`python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline` (C4, 72 views; setup + 3 steps).\n"
+                "`python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline` with `--profile-from-start off` (bench.py brackets\n"
+                "exactly the K timed steps with cudaProfilerStart/Stop): C4, 72 views, 2 steps.\n"
                 "Times are cold-cache and serialised: compare SHARES, not absolutes.\n\n"
                 "| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
         for k in sorted(per, key=lambda k: -per[k][1]):
@@ -66,7 +67,7 @@ if os.path.exists(rep):
     summ = {}
     with open(os.path.join(out_dir, f"{tag}_ncu_full.md"), "w") as f:
         f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` of one bench step\n"
-                "(`python bench.py --steps 1 --warmup 1 --views 8`, C4 mesh, 8 views = 5 529 600 rays per launch).\n\n")
+                "(`python bench.py --steps 1 --warmup 3 --views 8 --profile-from-start off`, C4 mesh, 8 views = 5 529 600 rays per launch).\n\n")
         for r in rows[2:]:
             name = short(r[hdr.index("Kernel Name")])
             f.write(f"## `{name}`\n\n| metric | value |\n|---|---:|\n")
