@@ -6,8 +6,8 @@
 // Pipeline (all on the caller's stream, no host sync):
 //   1 bounds   : per-triangle AABB centroid -> scene centroid bounds + largest |coordinate|
 //                (warp shuffle + ordered-uint atomics)
-//   2 morton   : 63-bit Morton code (21 bits/axis) of the normalised centroid
-//   3 sort     : LSD radix sort of (code, triangle id) pairs
+//   2 morton   : key = (39-bit Morton code of the normalised centroid, 13 bits/axis) << 25 | triangle id
+//   3 sort     : hand-written LSD radix sort of the unique 64-bit keys (radix_sort.cuh)
 //   4 topology : Karras 2012 -- one thread per internal node finds its key range and split
 //   5 fit      : bottom-up AABB union with atomic arrival counters
 //   6 emit     : traversal layout (below)
@@ -16,6 +16,7 @@
 //  35 % slower than the binary layout on the benchmark meshes -- see DESIGN.md -- so it is not kept.)
 #pragma once
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace drt {
 
@@ -107,20 +108,21 @@ __global__ void centroid_bounds_kernel(const int32_t* __restrict__ F, const floa
     }
 }
 
-__device__ __forceinline__ uint64_t spread21(uint32_t v)
+constexpr int kIndexBits = 25;              // up to 33 554 432 triangles
+constexpr int kMortonBitsPerAxis = 13;      // 8192 cells per axis
+
+__device__ __forceinline__ uint64_t spread13(uint32_t v)
 {
-    uint64_t x = v & 0x1fffffu;
-    x = (x | x << 32) & 0x1f00000000ffffull;
-    x = (x | x << 16) & 0x1f0000ff0000ffull;
-    x = (x | x << 8) & 0x100f00f00f00f00full;
-    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-    x = (x | x << 2) & 0x1249249249249249ull;
+    uint64_t x = v & 0x1fffu;
+    x = (x | x << 16) & 0x0000ff0000ffull;   // keep generous masks: only 13 input bits are live
+    x = (x | x << 8) & 0x00f00f00f00full;
+    x = (x | x << 4) & 0x0c30c30c30c3ull;
+    x = (x | x << 2) & 0x249249249249ull;
     return x;
 }
 
 __global__ void morton_kernel(const int32_t* __restrict__ F, const float* __restrict__ V, int nF,
-                              const unsigned* __restrict__ scene, uint64_t* __restrict__ keys,
-                              uint32_t* __restrict__ vals)
+                              const unsigned* __restrict__ scene, uint64_t* __restrict__ keys)
 {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nF) return;
@@ -133,20 +135,20 @@ __global__ void morton_kernel(const int32_t* __restrict__ F, const float* __rest
         float c = 0.5f * lo[k] + 0.5f * hi[k];
         float ext = mx - mn;
         float u = ext > 0.f ? (c - mn) / ext : 0.f;
-        float s = fminf(fmaxf(u * 2097152.f, 0.f), 2097151.f);
+        float s = fminf(fmaxf(u * 8192.f, 0.f), 8191.f);
         q[k] = (uint32_t)s;
     }
-    keys[f] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
-    vals[f] = (uint32_t)f;
+    uint64_t morton = (spread13(q[0]) << 2) | (spread13(q[1]) << 1) | spread13(q[2]);
+    keys[f] = (morton << kIndexBits) | (uint64_t)(uint32_t)f;
 }
 
-// Karras delta: length of the common prefix of keys i and j (index tie-break), -1 out of range
+__device__ __forceinline__ int key_tri(uint64_t key) { return (int)(key & ((1ull << kIndexBits) - 1)); }
+
+// Karras delta: length of the common prefix of the (unique) keys i and j, -1 out of range
 __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, uint64_t ki, int j)
 {
     if (j < 0 || j >= n) return -1;
-    uint64_t kj = keys[j];
-    if (ki == kj) return 64 + __clz(i ^ j);
-    return __clzll((long long)(ki ^ kj));
+    return __clzll((long long)(ki ^ keys[j]));
 }
 
 // node numbering during the build: internal i -> i (0..n-2), leaf k -> n-1+k
@@ -180,14 +182,14 @@ __global__ void topology_kernel(const uint64_t* __restrict__ keys, int n, int2* 
 }
 
 // bottom-up fit; box arrays indexed by build numbering; flags[n-1] zeroed by the caller
-__global__ void fit_kernel(const int32_t* __restrict__ F, const float* __restrict__ V, const uint32_t* __restrict__ vals,
+__global__ void fit_kernel(const int32_t* __restrict__ F, const float* __restrict__ V, const uint64_t* __restrict__ keys,
                            int n, const int2* __restrict__ children, const int* __restrict__ parent,
                            float4* __restrict__ blo, float4* __restrict__ bhi, int* __restrict__ flags)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     float lo[3], hi[3];
-    tri_box(F, V, (int)vals[k], lo, hi);
+    tri_box(F, V, key_tri(keys[k]), lo, hi);
     int me = n - 1 + k;
     blo[me] = make_float4(lo[0], lo[1], lo[2], 0.f);
     bhi[me] = make_float4(hi[0], hi[1], hi[2], 0.f);
@@ -241,11 +243,11 @@ __global__ void emit_nodes_kernel(int n, const int2* __restrict__ children, cons
 }
 
 __global__ void emit_tris_kernel(const int32_t* __restrict__ F, const float* __restrict__ V,
-                                 const uint32_t* __restrict__ vals, int n, double2* __restrict__ tris)
+                                 const uint64_t* __restrict__ keys, int n, double2* __restrict__ tris)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    int f = (int)vals[k];
+    int f = key_tri(keys[k]);
     const float* pa = &V[3 * (size_t)F[3 * f]];
     const float* pb = &V[3 * (size_t)F[3 * f + 1]];
     const float* pc = &V[3 * (size_t)F[3 * f + 2]];

@@ -1,6 +1,4 @@
 // capi.cu -- extern "C" boundary of libdrt_b200.so (see include/drt_b200.h).
-#include <cub/device/device_radix_sort.cuh>
-
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -87,8 +85,7 @@ struct drt_bvh {
     float* V32 = nullptr;   size_t capV = 0;     // [nV*3]
     // build scratch
     uint64_t* keys = nullptr;  size_t capK = 0;  // 2*nF (double buffer)
-    uint32_t* vals = nullptr;  size_t capVa = 0; // 2*nF
-    void* cub_tmp = nullptr;   size_t cub_bytes = 0;
+    unsigned* sort_table = nullptr; size_t capSt = 0; // 256 x tiles digit counters of the radix sort
     int2* children = nullptr;  size_t capCh = 0; // nF-1
     int* parent = nullptr;     size_t capP = 0;  // 2nF-1
     float4* blo = nullptr;     size_t capBl = 0; // 2nF-1
@@ -100,7 +97,7 @@ struct drt_bvh {
     unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
     int work_slot = 0;
     int fwd_blocks_per_sm = 0;                   // occupancy of trace_fwd_persistent_kernel
-    uint32_t* sorted_vals = nullptr;             // points into vals (which half holds the sorted ids)
+    uint64_t* sorted_keys = nullptr;             // the half of `keys` that holds the sorted (Morton, id) keys
     // traversal data
     float4* nodes = nullptr;   size_t capN = 0;
     double2* tris = nullptr;   size_t capT = 0;
@@ -147,10 +144,10 @@ int fit_and_emit(drt_bvh* b, cudaStream_t st)
     const int n = b->nF;
     if (n <= 0) return DRT_OK;
     if (n > 1) CU(cudaMemsetAsync(b->flags, 0, sizeof(int) * (size_t)(n - 1), st));
-    fit_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_vals, n, b->children, b->parent, b->blo, b->bhi,
+    fit_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_keys, n, b->children, b->parent, b->blo, b->bhi,
                                                     b->flags); ++g_launches;
     emit_nodes_kernel<<<blocks_for(n > 1 ? n - 1 : 1, 256), 256, 0, st>>>(n, b->children, b->blo, b->bhi, b->scene, b->nodes); ++g_launches;
-    emit_tris_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_vals, n, b->tris); ++g_launches;
+    emit_tris_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_keys, n, b->tris); ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
 }
@@ -163,7 +160,7 @@ int build_tree(drt_bvh* b, cudaStream_t st)
     if (n <= 0) return DRT_OK;
     int rc;
     if ((rc = ensure(b->keys, b->capK, 2 * (size_t)n))) return rc;
-    if ((rc = ensure(b->vals, b->capVa, 2 * (size_t)n))) return rc;
+    if ((rc = ensure(b->sort_table, b->capSt, 256 * (size_t)sort_tiles(n)))) return rc;
     if ((rc = ensure(b->children, b->capCh, (size_t)n))) return rc;
     if ((rc = ensure(b->parent, b->capP, 2 * (size_t)n))) return rc;
     if ((rc = ensure(b->blo, b->capBl, 2 * (size_t)n))) return rc;
@@ -174,25 +171,11 @@ int build_tree(drt_bvh* b, cudaStream_t st)
 
     init_scene_kernel<<<1, 32, 0, st>>>(b->scene, false); ++g_launches;
     centroid_bounds_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene); ++g_launches;
-    morton_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene, b->keys, b->vals); ++g_launches;
-    // (code, id) pairs: LSD radix sort over the 63 live key bits
-    cub::DoubleBuffer<uint64_t> dk(b->keys, b->keys + n);
-    cub::DoubleBuffer<uint32_t> dv(b->vals, b->vals + n);
-    size_t need = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, 63, st));
-    if (need > b->cub_bytes) {
-        if (b->cub_tmp) CU(cudaFree(b->cub_tmp));
-        b->cub_tmp = nullptr;
-        b->cub_bytes = 0;
-        CU(cudaMalloc(&b->cub_tmp, need + need / 4));
-        b->cub_bytes = need + need / 4;
-    }
-    size_t tmp_bytes = b->cub_bytes;
-    CU(cub::DeviceRadixSort::SortPairs(b->cub_tmp, tmp_bytes, dk, dv, n, 0, 63, st));
-    g_launches += 1;  // the sort is counted as ONE launch (its internal passes are CUB's)
-    b->sorted_vals = dv.Current();
+    morton_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene, b->keys); ++g_launches;
+    // unique keys (Morton << 25 | id): keys-only LSD radix sort over the Morton bits
+    b->sorted_keys = sort_keys_u64(b->keys, n, kIndexBits, b->sort_table, st, &g_launches);
     if (n > 1) {
-        topology_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>(dk.Current(), n, b->children, b->parent);
+        topology_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>(b->sorted_keys, n, b->children, b->parent);
         ++g_launches;
     }
     CU(cudaGetLastError());
@@ -218,6 +201,7 @@ int build_common(drt_bvh* b, const int32_t* F, int nF, const float* V32, const d
 {
     if (!b) return fail(DRT_ERR_INVALID, "drt_bvh_build: null handle");
     if (nF < 0 || nV < 0) return fail(DRT_ERR_INVALID, "drt_bvh_build: negative size (nF=%d, nV=%d)", nF, nV);
+    if (nF > (1 << kIndexBits)) return fail(DRT_ERR_INVALID, "drt_bvh_build: %d triangles exceed the supported %d", nF, 1 << kIndexBits);
     if ((nF > 0 && !F) || (nV > 0 && !V32 && !V64)) return fail(DRT_ERR_INVALID, "drt_bvh_build: null F or V");
     if (nF > 0 && nV == 0) return fail(DRT_ERR_INVALID, "drt_bvh_build: faces without vertices");
     DeviceGuard g(b->device);
@@ -273,7 +257,7 @@ int drt_bvh_destroy(drt_bvh* b)
     if (!b) return DRT_OK;
     DeviceGuard g(b->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {b->listA, b->listB, b->work, b->F, b->V32, b->keys, b->vals, b->cub_tmp, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
+    void* ptrs[] = {b->listA, b->listB, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete b;

@@ -249,3 +249,32 @@ def test_both_forward_kernels_pass_the_parity_suite(kernel):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
                         "golden or full_view or refit or all_rays_miss or large_batch"], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_fused_ray_loss_matches_reference_expression(cuda_device):
+    """drt_b200.losses.ray_loss against the reference's ray_loss expression (optim.py:96-106) evaluated
+    with torch autograd on top of render_transparent."""
+    from drt_b200 import losses, views
+    v, f = load_mesh("hand_vh")
+    R, sc = _scene(v, f, cuda_device)
+    cams = views.turntable_cameras(v, 128, 128, 72)
+    o, d = views.generate_ray(128, 128, cams[20][3], cams[20][2], device=cuda_device)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    with torch.no_grad():
+        oo, od, mk = sc.render_transparent(o, d)
+    screen = (oo + od * 80 + 0.5 * torch.randn(o.shape, generator=g, dtype=torch.float64).to(cuda_device)).contiguous()
+    valid = (torch.rand(len(o), generator=g) > 0.1).to(cuda_device)
+    Va = sc.vertices.clone().requires_grad_(True)
+    sc.update_verticex(Va)
+    out_ori, out_dir, mask = sc.render_transparent(o, d)
+    target = screen - out_ori.detach()
+    target = target / target.norm(dim=1, keepdim=True)
+    ref = ((out_dir - target)[valid * mask[:, 0]]).pow(2).sum()
+    (3.0 * ref).backward()
+    Vb = sc.vertices.detach().clone().requires_grad_(True)
+    sc.update_verticex(Vb)
+    mine = losses.ray_loss(sc, o, d, screen, valid)
+    (3.0 * mine).backward()
+    assert abs(mine.item() - ref.item()) <= 1e-12 * abs(ref.item())
+    pv, gl = grad_rel_err(Vb.grad.cpu().numpy(), Va.grad.cpu().numpy())
+    assert pv < 1e-10 and gl < 1e-12, (pv, gl)
