@@ -59,11 +59,11 @@ def optimize(vertices0, faces, data, hp, iters, log_every=10, fused_loss=True):
         loss = (hp["ray_w"] * 217.5 / data.resy / data.resy * ray_loss + hp["vh_w"] * 217.5 / data.resy * vh_loss
                 + hp["sm_w"] * scene.mean_len / 10 * sm_loss)                      # optim.py:127-129
         loss.backward()
-        opt.step()
-        history.append((float(ray_loss), float(vh_loss), float(sm_loss)))
-        if log_every and it % log_every == 0:
+        history.append((ray_loss.item(), vh_loss.item(), sm_loss.item()))
+        if log_every and it % log_every == 0:  # before the step, like optim.py:212-215 (foreach-SGD rewrites .grad in place)
             print(f"Iteration {it}: ray={history[-1][0]:g} vh={history[-1][1]:g} sm={history[-1][2]:g} "
                   f"maxgrad={parameter.grad.abs().max():g}", flush=True)
+        opt.step()
     return scene, history
 
 
@@ -73,10 +73,13 @@ def main():
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--res", type=int, nargs=2, default=[240, 320])
     ap.add_argument("--views", type=int, default=24)
+    ap.add_argument("--lr", type=float, default=0.1)
+    ap.add_argument("--momentum", type=float, default=0.95)
+    ap.add_argument("--scale", type=float, default=0.6, help="amplitude (mm) of the target perturbation")
     args = ap.parse_args()
-    hp = {"IOR": 1.4723, "ray_w": 40, "sm_w": 0.08, "vh_w": 2e-3, "momentum": 0.95, "start_lr": 0.1}  # config.py:18-39
+    hp = {"IOR": 1.4723, "ray_w": 40, "sm_w": 0.08, "vh_w": 2e-3, "momentum": args.momentum, "start_lr": args.lr}  # config.py:18-39
     v, f = configs.load_mesh(args.mesh)
-    target = configs.perturbed_target_mesh(v, scale=0.6)
+    target = configs.perturbed_target_mesh(v, scale=args.scale)
     data = synthetic_data.SyntheticData(target, f, args.res[0], args.res[1], n_views=args.views, num_view=args.views, int_ior=hp["IOR"])
     t0 = time.time()
     scene, hist = optimize(v, f, data, hp, args.iters)
