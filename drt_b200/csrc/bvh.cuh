@@ -15,6 +15,8 @@
 // (A 4-wide collapse of this tree was built and measured on B200: +40 % executed instructions and
 //  35 % slower than the binary layout on the benchmark meshes -- see DESIGN.md -- so it is not kept.)
 #pragma once
+#include <cuda/atomic>
+
 #include "common.cuh"
 #include "radix_sort.cuh"
 
@@ -196,9 +198,9 @@ __global__ void fit_kernel(const int32_t* __restrict__ F, const float* __restric
     if (n == 1) return;
     int cur = parent[me];
     while (cur >= 0) {
-        __threadfence();
-        if (atomicAdd(&flags[cur], 1) == 0) return;  // first arrival: the sibling will finish this node
-        __threadfence();
+        // one acq_rel RMW at device scope: releases this thread's box store, acquires the sibling's
+        cuda::atomic_ref<int, cuda::thread_scope_device> arrived(flags[cur]);
+        if (arrived.fetch_add(1, cuda::memory_order_acq_rel) == 0) return;  // first arrival: the sibling finishes this node
         int2 ch = children[cur];
         // volatile-style reads through L2: the sibling's stores were fenced before its atomic
         float4 l0 = __ldcg(&blo[ch.x]), h0 = __ldcg(&bhi[ch.x]);

@@ -2,10 +2,12 @@
 //
 // Keys are (39-bit Morton code << 25) | triangle index, so they are unique, carry their own payload
 // and arrive sorted by their low 25 bits; only the passes that touch Morton bits are run (bits 24..63,
-// five 8-bit passes).  Each pass is three launches:
+// five 8-bit passes).  Each pass is two launches:
 //   hist    : per-tile digit histograms, digit-major [256][tiles]
-//   scan    : one block, exclusive scan over the digit-major table (<= 256 x a few hundred entries)
-//   scatter : per tile, STABLE ranks from warp match_any + per-warp digit counters in shared memory
+//   scatter : every block first derives its global bases from the raw table (thread = digit: total of
+//             the digit over all tiles, block-wide exclusive scan over digits, plus the digit's counts
+//             in the tiles before this one -- <= 256 x tiles reads, L2 resident), then computes STABLE
+//             ranks from warp match_any + per-warp digit counters in shared memory and scatters
 // A tile is 256 threads x 8 keys; stability needs the (warp, round, lane) order to equal the key order,
 // hence the warp-blocked item assignment below.
 #pragma once
@@ -40,51 +42,37 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint64_t*
     table[threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of table[0..m), one block of 1024 threads, in place
-__global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned* __restrict__ table, int m)
-{
-    __shared__ unsigned warp_sum[32];
-    __shared__ unsigned carry;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < m; base += 1024) {
-        int i = base + threadIdx.x;
-        unsigned v = i < m ? table[i] : 0u;
-        unsigned x = v;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            unsigned y = __shfl_up_sync(0xffffffffu, x, s);
-            if (lane >= s) x += y;
-        }
-        if (lane == 31) warp_sum[w] = x;
-        __syncthreads();
-        if (w == 0) {
-            unsigned t = warp_sum[lane];
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                unsigned y = __shfl_up_sync(0xffffffffu, t, s);
-                if (lane >= s) t += y;
-            }
-            warp_sum[lane] = t;
-        }
-        __syncthreads();
-        unsigned off = carry + (w ? warp_sum[w - 1] : 0u);
-        if (i < m) table[i] = off + x - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = off + x;
-        __syncthreads();
-    }
-}
-
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
                                                                     int n, int shift, int tiles,
                                                                     const unsigned* __restrict__ table)
 {
     __shared__ unsigned cnt[kSortWarps][256];  // per-warp digit counts, then exclusive bases across warps
+    __shared__ unsigned gbase[256];            // global base of every digit for THIS tile
+    __shared__ unsigned wsum[kSortWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     for (int j = threadIdx.x; j < kSortWarps * 256; j += kSortThreads) (&cnt[0][0])[j] = 0;
+    {   // thread = digit d: total over tiles and the part that belongs to earlier tiles
+        const unsigned* row = table + threadIdx.x * tiles;
+        unsigned total = 0, before = 0;
+        for (int t = 0; t < tiles; ++t) {
+            unsigned c = row[t];
+            before += t < (int)blockIdx.x ? c : 0u;
+            total += c;
+        }
+        unsigned x = total;  // block-wide exclusive scan of `total` over the 256 digits
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, x, sft);
+            if (lane >= sft) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        unsigned off = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) off += w < warp ? wsum[w] : 0u;
+        gbase[threadIdx.x] = off + x - total + before;
+    }
     __syncthreads();
     uint64_t key[kSortItems];
     unsigned rank[kSortItems];
@@ -107,7 +95,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
     }
     __syncthreads();
     {  // exclusive prefix over warps for each digit (thread = digit), plus the tile's global base
-        unsigned d = threadIdx.x, run = table[d * tiles + blockIdx.x];
+        unsigned d = threadIdx.x, run = gbase[d];
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
             unsigned c = cnt[w][d];
@@ -126,7 +114,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64
 inline int sort_tiles(int n) { return (n + kSortTile - 1) / kSortTile; }
 
 // Sorts n keys on bits [first_bit, 64); buf holds 2n keys (keys in the first half on entry), table holds
-// 256 * sort_tiles(n) counters.  Returns the half that holds the sorted keys.  5 passes x 3 launches.
+// 256 * sort_tiles(n) counters.  Returns the half that holds the sorted keys.  5 passes x 2 launches.
 inline uint64_t* sort_keys_u64(uint64_t* buf, int n, int first_bit, unsigned* table, cudaStream_t st, unsigned long long* launches)
 {
     uint64_t* a = buf;
@@ -134,9 +122,8 @@ inline uint64_t* sort_keys_u64(uint64_t* buf, int n, int first_bit, unsigned* ta
     const int tiles = sort_tiles(n);
     for (int shift = first_bit & ~7; shift < 64; shift += 8) {
         sort_hist_kernel<<<tiles, kSortThreads, 0, st>>>(a, n, shift, tiles, table);
-        sort_scan_kernel<<<1, 1024, 0, st>>>(table, 256 * tiles);
         sort_scatter_kernel<<<tiles, kSortThreads, 0, st>>>(a, b, n, shift, tiles, table);
-        if (launches) *launches += 3;
+        if (launches) *launches += 2;
         uint64_t* t = a; a = b; b = t;
     }
     return a;
