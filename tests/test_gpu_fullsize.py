@@ -1,0 +1,96 @@
+"""Full BASELINE size (C4: 50 248 triangles, 72 views x 960x720 = 49 766 400 rays) through properties
+that need no oracle run: per-ray independence (permutation / sharding invariance, bit-exact),
+output invariants, linearity of the backward pass, view-shard sums."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c4(cuda_device):
+    import drt_b200.DiffRender as R
+    from drt_b200 import configs, views
+    free, _ = torch.cuda.mem_get_info(cuda_device)
+    if free < 24e9:
+        pytest.skip("needs ~20 GB of free device memory")
+    cfg = configs.make("C4")
+    R.intIOR = configs.INT_IOR
+    sc = R.Scene(vertices=cfg["vertices"], faces=cfg["faces"], cuda_device=cuda_device.index or 0)
+    o, d = views.view_batch(cfg["cams"], cfg["resy"], cfg["resx"], device=cuda_device)
+    V = sc.vertices.clone().requires_grad_(True)
+    sc.update_verticex(V)
+    out = sc.render_transparent(o, d)
+    return dict(cfg=cfg, scene=sc, V=V, o=o, d=d, out=out)
+
+
+def test_full_size_output_invariants(c4):
+    out_ori, out_dir, mask = c4["out"]
+    n = c4["o"].shape[0]
+    assert n == 49766400 and mask.shape == (n, 3)
+    m = mask[:, 0]
+    assert torch.equal(m, mask[:, 1]) and torch.equal(m, mask[:, 2])
+    frac = m.float().mean().item()
+    assert 0.05 < frac < 0.09                              # 6.8 % valid two-bounce paths on this framing
+    assert not out_ori[~m].any() and not out_dir[~m].any()  # zeros where invalid (DiffRender.py:421-423)
+    nrm = out_dir[m].norm(dim=1)
+    assert (nrm - 1).abs().max().item() < 1e-14             # Refract renormalises (DiffRender.py:47)
+    assert torch.isfinite(out_ori).all() and torch.isfinite(out_dir).all()
+    # every valid exit point lies within the (slightly padded) bounding box of the mesh
+    v = c4["scene"].vertices.detach()
+    lo, hi = v.min(0).values - 1e-3, v.max(0).values + 1e-3
+    p = out_ori[m]
+    assert ((p >= lo) & (p <= hi)).all()
+    hit = c4["scene"].render_mask(c4["o"][: 4 * 691200], c4["d"][: 4 * 691200]) > 0
+    assert (hit | ~m[: 4 * 691200]).all()                   # mask implies a primary hit
+
+
+def test_full_size_permutation_and_sharding_invariance(c4):
+    """Rays are independent: any subset, in any order, must give bit-identical rows."""
+    sc, o, d = c4["scene"], c4["o"], c4["d"]
+    out_ori, out_dir, mask = c4["out"]
+    g = torch.Generator(device="cpu").manual_seed(0)
+    idx = torch.randint(0, o.shape[0], (3_000_000,), generator=g).to(o.device)    # > 2^20: wavefront path
+    oo, od, mk = sc.render_transparent(o[idx].contiguous(), d[idx].contiguous())
+    assert torch.equal(oo, out_ori[idx]) and torch.equal(od, out_dir[idx]) and torch.equal(mk, mask[idx])
+    small = idx[:50_000]                                                          # one-launch kernel path
+    oo, od, mk = sc.render_transparent(o[small].contiguous(), d[small].contiguous())
+    assert torch.equal(oo, out_ori[small]) and torch.equal(od, out_dir[small]) and torch.equal(mk, mask[small])
+    n_pix = 691200                                                                # one whole view = one shard unit
+    oo, od, mk = sc.render_transparent(o[5 * n_pix:6 * n_pix], d[5 * n_pix:6 * n_pix])
+    assert torch.equal(oo, out_ori[5 * n_pix:6 * n_pix]) and torch.equal(mk, mask[5 * n_pix:6 * n_pix])
+
+
+def test_full_size_backward_linearity_and_shard_sum(c4):
+    sc, V, o, d = c4["scene"], c4["V"], c4["o"], c4["d"]
+    out_ori, out_dir, mask = c4["out"]
+    n = o.shape[0]
+    g = torch.Generator(device="cpu").manual_seed(1)
+    # cheap structured upstream gradients (no 2.4 GB randn on the host)
+    w1 = torch.sin(torch.arange(n, device=o.device, dtype=torch.float64) * 1e-3).unsqueeze(1) * torch.tensor([[1.0, -2.0, 0.5]], device=o.device, dtype=torch.float64)
+    w2 = torch.cos(torch.arange(n, device=o.device, dtype=torch.float64) * 7e-4).unsqueeze(1) * torch.tensor([[0.3, 0.7, -1.1]], device=o.device, dtype=torch.float64)
+
+    def grad(gd, go=None):
+        V.grad = None
+        torch.autograd.backward([out_dir] if go is None else [out_dir, out_ori], [gd] if go is None else [gd, go], retain_graph=True)
+        return V.grad.clone()
+
+    g1, g2 = grad(w1), grad(w2)
+    g12 = grad(w1 + 2.0 * w2)
+    scale = g12.abs().max().item()
+    assert scale > 0 and (g12 - (g1 + 2.0 * g2)).abs().max().item() < 1e-11 * scale     # linear in the upstream gradient
+    g_ori = grad(torch.zeros_like(w1), w1)
+    assert g_ori.abs().max().item() > 0 and torch.isfinite(g_ori).all()
+    # sum over view shards == whole batch (what the multi-GPU all-reduce relies on)
+    n_pix, parts = 691200, torch.zeros_like(g1)
+    for r in range(8):
+        sel = torch.cat([torch.arange(k * n_pix, (k + 1) * n_pix, device=o.device) for k in range(r, 72, 8)])
+        Vr = sc.vertices.detach().clone().requires_grad_(True)
+        sc.update_verticex(Vr)
+        _, od, _ = sc.render_transparent(o[sel].contiguous(), d[sel].contiguous())
+        od.backward(w1[sel].contiguous())
+        parts += Vr.grad
+    sc.update_verticex(V)
+    assert (parts - g1).abs().max().item() < 1e-11 * g1.abs().max().item()
+    assert torch.isfinite(g1).all() and (g1.abs().sum(dim=1) > 0).float().mean().item() > 0.5   # most vertices receive gradient
