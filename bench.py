@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-views", type=int, default=36, help="views of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-chain-gpu", action="store_true", help="skip the supplementary R-GPU baseline")
     ap.add_argument("--refit", action="store_true", help="refit instead of rebuilding the BVH each step")
     return ap.parse_args()
 
@@ -354,6 +355,39 @@ def run_b200(args):
         assert abs(loss_host.item() - loss_val) <= 1e-6 * max(1.0, abs(loss_val)), (loss_host.item(), loss_val)
     sampler.stop()
 
+    # ---- R-GPU (supplementary, rank 0, N=1 only): the reference's approach on this same B200 --------------
+    # its PyTorch op chain + autograd (restated in oracle/chain_torch.py, checked against the reference goldens)
+    # with the query served by drt_closest_hit, one view per iteration as the reference does (optim.py:95).
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_ref_chain_gpu:
+        from oracle import chain_torch
+        Vr = scene.vertices.detach().clone().requires_grad_(True)
+        scene.update_verticex(Vr)
+        isect = lambda r6: scene.optix_mesh.intersect(r6)  # noqa: E731
+        faces_t = scene.faces
+        n_ref = min(6, len(cams))
+        t_ref = 0.0
+        for j in range(n_ref + 2):
+            cam = cams[(j * 7) % len(cams)]
+            o_v, d_v = views.generate_ray(resy, resx, cam[3], cam[2], device=dev)
+            scr_v = o_v + 50.0 * d_v
+            torch.cuda.synchronize(dev)
+            a, b = ev(), ev()
+            a.record()
+            Vr.grad = None
+            oo, od, mk = chain_torch.render_transparent(Vr, faces_t, o_v, d_v, isect, configs.INT_IOR)
+            tg = scr_v - oo.detach()
+            tg = tg / tg.norm(dim=1, keepdim=True)
+            ((od - tg)[mk[:, 0]]).pow(2).sum().backward()
+            b.record()
+            torch.cuda.synchronize(dev)
+            if j >= 2:
+                t_ref += a.elapsed_time(b)
+        ref_gpu = {"value": n_ref * n_pix / (t_ref * 1e-3), "unit": UNIT, "ms_per_view": t_ref / n_ref, "views": n_ref,
+                   "kind": "reference op chain (PyTorch autograd, oracle/chain_torch.py) + drt_closest_hit as the intersector, "
+                           "one view per iteration; supplementary, not the driver's reference arm"}
+        scene.update_verticex(V)
+
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -396,7 +430,7 @@ def run_b200(args):
                        "int_ior": configs.INT_IOR, "valid_frac_rank0": valid_frac},
             "phases_ms": {"bvh_build": t_build_ms, "fwd": t_fwd_ms, "loss_grad": phases[2], "bwd": t_bwd_ms, "allreduce": t_ar_ms},
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "loss": loss_val, "grad_norm": grad_norm,
         }
         print(json.dumps(out), flush=True)
