@@ -51,6 +51,7 @@ constexpr int64_t kSimpleMaxRays = 1 << 20;
 struct Tuning {
     bool simple_fwd = false;
     bool force_wavefront = false;
+    bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
     int thresh = 32;
     int minb = 8;
     Tuning()
@@ -61,6 +62,8 @@ struct Tuning {
 
         const char* t = getenv("DRT_FWD_THRESH");
         if (t && atoi(t) >= 1 && atoi(t) <= 32) thresh = atoi(t);
+        const char* z = getenv("DRT_BULK_ZERO");
+        if (z && !strcmp(z, "0")) bulk = false;
         const char* m = getenv("DRT_Q_MINB");
         if (m) minb = atoi(m);
         if (minb != 4 && minb != 6 && minb != 8 && minb != 10) minb = 8;
@@ -360,7 +363,9 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
         int* countM = countL + 1;
         const int thresh = tuning().thresh;
         const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
-        EntryJob j1{origin, dir, out_ori, out_dir, mask3, hit1, b->listA, countL};
+        // bulk zero-fill needs 16-byte aligned output rows for every multiple-of-32 ray index
+        const bool bulk_ok = tuning().bulk && !(((uintptr_t)out_ori | (uintptr_t)out_dir | (uintptr_t)mask3 | (uintptr_t)hit1) & 15u);
+        EntryJob j1{bulk_ok ? reinterpret_cast<const ZeroTile*>(1) : nullptr, false, origin, dir, out_ori, out_dir, mask3, hit1, b->listA, countL};
         const int minb = tuning().minb;
         const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
 #define DRT_LAUNCH_Q(KERNEL, ...)                                                           \
