@@ -51,6 +51,7 @@ constexpr int64_t kSimpleMaxRays = 1 << 20;
 struct Tuning {
     bool simple_fwd = false;
     bool force_wavefront = false;
+    bool one_launch = false;  // DRT_ONE_LAUNCH=1: the cooperative single-launch variant (measured 1.5 % slower: spills)
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
     int thresh = 32;
     int minb = 8;
@@ -62,6 +63,8 @@ struct Tuning {
 
         const char* t = getenv("DRT_FWD_THRESH");
         if (t && atoi(t) >= 1 && atoi(t) <= 32) thresh = atoi(t);
+        const char* ol = getenv("DRT_ONE_LAUNCH");
+        if (ol && !strcmp(ol, "1")) one_launch = true;
         const char* z = getenv("DRT_BULK_ZERO");
         if (z && !strcmp(z, "0")) bulk = false;
         const char* m = getenv("DRT_Q_MINB");
@@ -99,7 +102,8 @@ struct drt_bvh {
     int4* listB = nullptr;     size_t capLB = 0; // wavefront list M: entries of L that survive both refractions
     unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
     int work_slot = 0;
-    int fwd_blocks_per_sm = 0;                   // occupancy of trace_fwd_persistent_kernel
+    int fused_blocks_per_sm = 0;                 // co-resident blocks of wf_fused_kernel<8> (0: no cooperative launch)
+    int fused6_blocks_per_sm = 0;                // same for the 80-register variant
     uint64_t* sorted_keys = nullptr;             // the half of `keys` that holds the sorted (Morton, id) keys
     // traversal data
     float4* nodes = nullptr;   size_t capN = 0;
@@ -250,6 +254,12 @@ int drt_bvh_create(int device, drt_bvh** out)
     CU(cudaMalloc(&b->scene, 8 * sizeof(unsigned)));
     CU(cudaMemset(b->scene, 0, 8 * sizeof(unsigned)));
     CU(cudaMalloc(&b->work, kWorkSlots * sizeof(unsigned long long)));
+    {
+        int coop = 0;
+        CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        if (coop) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->fused_blocks_per_sm, wf_fused_kernel<8>, 128, 0));
+        if (coop) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->fused6_blocks_per_sm, wf_fused_kernel<6>, 128, 0));
+    }
 
     *out = b;
     return DRT_OK;
@@ -362,12 +372,26 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
         int* countL = (int*)(ctl + 3);
         int* countM = countL + 1;
         const int thresh = tuning().thresh;
-        const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
         // bulk zero-fill needs 16-byte aligned output rows for every multiple-of-32 ray index
         const bool bulk_ok = tuning().bulk && !(((uintptr_t)out_ori | (uintptr_t)out_dir | (uintptr_t)mask3 | (uintptr_t)hit1) & 15u);
+        const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
         EntryJob j1{bulk_ok ? reinterpret_cast<const ZeroTile*>(1) : nullptr, false, origin, dir, out_ori, out_dir, mask3, hit1, b->listA, countL};
         const int minb = tuning().minb;
         const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
+        if (tuning().one_launch && b->fused_blocks_per_sm > 0) {
+            // the whole wavefront as ONE cooperative launch (grid-wide barriers between the stages)
+            FwdArgs fa{b->view(), V64, origin, dir, (int)N, ext_ior, int_ior, out_ori, out_dir, mask3, hit1, b->listA, b->listB,
+                       (int4*)rec, rec_count, ctl, thresh, bulk_ok ? 1 : 0};
+            void* kargs[] = {&fa};
+            const bool six = minb == 6 && b->fused6_blocks_per_sm > 0;
+            const int per_sm = six ? b->fused6_blocks_per_sm : b->fused_blocks_per_sm;
+            const int cg_grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * per_sm);
+            CU(cudaLaunchCooperativeKernel(six ? (void*)wf_fused_kernel<6> : (void*)wf_fused_kernel<8>, dim3(cg_grid), dim3(128),
+                                           kargs, 0, st));
+            ++g_launches;
+            CU(cudaGetLastError());
+            return DRT_OK;
+        }
 #define DRT_LAUNCH_Q(KERNEL, ...)                                                           \
     do {                                                                                    \
         if (minb == 10) KERNEL<10><<<pg, 128, 0, st>>>(__VA_ARGS__);                        \

@@ -182,13 +182,13 @@ __global__ void __launch_bounds__(128, MINB) wf_q1_kernel(BvhView B, EntryJob jo
 }
 
 // ---- R1: refraction at the entry hit, dense over L ------------------------------------------------
-__global__ void __launch_bounds__(128) wf_r1_kernel(BvhView B, const double* __restrict__ V64,
-                                                    const double* __restrict__ origin, const double* __restrict__ dir,
-                                                    double ext_ior, double int_ior, double* __restrict__ out_ori,
-                                                    double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
-                                                    int4* __restrict__ L, const int* __restrict__ countL)
+__device__ __forceinline__ void r1_body(const BvhView& B, const double* __restrict__ V64,
+                                        const double* __restrict__ origin, const double* __restrict__ dir,
+                                        double ext_ior, double int_ior, double* __restrict__ out_ori,
+                                        double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
+                                        int4* __restrict__ L, const int* countL)
 {
-    const int n = *countL;
+    const int n = *(volatile const int*)countL;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         int4 e = L[k];
         const int64_t i = e.x;
@@ -204,6 +204,15 @@ __global__ void __launch_bounds__(128) wf_r1_kernel(BvhView B, const double* __r
             st3(out_dir + 3 * i, d1);
         }
     }
+}
+
+__global__ void __launch_bounds__(128) wf_r1_kernel(BvhView B, const double* __restrict__ V64,
+                                                    const double* __restrict__ origin, const double* __restrict__ dir,
+                                                    double ext_ior, double int_ior, double* __restrict__ out_ori,
+                                                    double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
+                                                    int4* __restrict__ L, const int* __restrict__ countL)
+{
+    r1_body(B, V64, origin, dir, ext_ior, int_ior, out_ori, out_dir, mask3, L, countL);
 }
 
 // ---- Q2 ------------------------------------------------------------------------------------------
@@ -233,13 +242,12 @@ __global__ void __launch_bounds__(128, MINB) wf_q2_kernel(BvhView B, ExitJob job
 }
 
 // ---- R2: refraction at the exit hit, dense over L; survivors -> M ---------------------------------
-__global__ void __launch_bounds__(128) wf_r2_kernel(BvhView B, const double* __restrict__ V64, double ext_ior,
-                                                    double int_ior, double* __restrict__ out_ori,
-                                                    double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
-                                                    const int4* __restrict__ L, const int* __restrict__ countL,
-                                                    int4* __restrict__ M, int* __restrict__ countM)
+__device__ __forceinline__ void r2_body(const BvhView& B, const double* __restrict__ V64, double ext_ior,
+                                        double int_ior, double* __restrict__ out_ori,
+                                        double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
+                                        const int4* L, const int* countL, int4* __restrict__ M, int* __restrict__ countM)
 {
-    const int n = *countL;
+    const int n = *(volatile const int*)countL;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const int4 e = L[k];
         const int64_t i = e.x;
@@ -261,6 +269,15 @@ __global__ void __launch_bounds__(128) wf_r2_kernel(BvhView B, const double* __r
         int slot = warp_append<>(countM, alive);
         if (slot >= 0) M[slot] = e;
     }
+}
+
+__global__ void __launch_bounds__(128) wf_r2_kernel(BvhView B, const double* __restrict__ V64, double ext_ior,
+                                                    double int_ior, double* __restrict__ out_ori,
+                                                    double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
+                                                    const int4* __restrict__ L, const int* __restrict__ countL,
+                                                    int4* __restrict__ M, int* __restrict__ countM)
+{
+    r2_body(B, V64, ext_ior, int_ior, out_ori, out_dir, mask3, L, countL, M, countM);
 }
 
 // ---- Q3 ------------------------------------------------------------------------------------------
@@ -300,6 +317,60 @@ __global__ void __launch_bounds__(128, MINB) wf_q3_kernel(BvhView B, OcclusionJo
                                                     unsigned long long* work, int thresh)
 {
     persistent_query<true>(B, job, *countM, work, thresh);
+}
+
+// ---- all five stages in ONE cooperative launch ------------------------------------------------------
+// Same stage bodies, separated by grid-wide barriers instead of kernel boundaries: one launch per
+// render_transparent call, no inter-kernel gaps, the list counters never leave the device.
+struct FwdArgs {
+    BvhView B;
+    const double* V64;
+    const double* origin;
+    const double* dir;
+    int N;
+    double ext_ior, int_ior;
+    double* out_ori;
+    double* out_dir;
+    uint8_t* mask3;
+    uint8_t* hit1;
+    int4* L;
+    int4* M;
+    int4* rec;
+    int* rec_count;
+    unsigned long long* ctl;  // [0..2] work counters of Q1,Q2,Q3; [3] = {countL, countM}
+    int thresh;
+    int bulk;
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) wf_fused_kernel(FwdArgs a)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ ZeroTile zt;
+    for (int j = threadIdx.x; j < 768 / 4; j += blockDim.x) reinterpret_cast<unsigned*>(zt.z)[j] = 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    int* countL = reinterpret_cast<int*>(a.ctl + 3);
+    int* countM = countL + 1;
+    {
+        EntryJob j{a.bulk ? &zt : nullptr, false, a.origin, a.dir, a.out_ori, a.out_dir, a.mask3, a.hit1, a.L, countL};
+        persistent_query<false>(a.B, j, a.N, a.ctl + 0, a.thresh);
+    }
+    grid.sync();
+    r1_body(a.B, a.V64, a.origin, a.dir, a.ext_ior, a.int_ior, a.out_ori, a.out_dir, a.mask3, a.L, countL);
+    grid.sync();
+    {
+        ExitJob j{a.out_ori, a.out_dir, a.L};
+        persistent_query<false>(a.B, j, *(volatile int*)countL, a.ctl + 1, a.thresh);
+    }
+    grid.sync();
+    r2_body(a.B, a.V64, a.ext_ior, a.int_ior, a.out_ori, a.out_dir, a.mask3, a.L, countL, a.M, countM);
+    grid.sync();
+    {
+        OcclusionJob j{a.out_ori, a.out_dir, a.mask3, a.M, a.rec, a.rec_count};
+        persistent_query<true>(a.B, j, *(volatile int*)countM, a.ctl + 2, a.thresh);
+    }
 }
 
 }  // namespace drt
