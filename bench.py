@@ -4,9 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config C4] [--impl reference]
 
 A step = one optim.py-shaped ray iteration over the whole view set of the config:
-    Scene.update_verticex (BVH rebuild, DiffRender.py:378-380)  ->  Scene.render_transparent (fused
-    forward kernel)  ->  ray_loss gradient (optim.py:96-106)  ->  backward kernel  ->  [N>1: NCCL
-    all-reduce of grad_V].  Views are sharded over ranks (view k -> rank k mod N), mesh/BVH replicated.
+    Scene.update_verticex (BVH rebuild, DiffRender.py:378-380)  ->  drt_b200.losses.ray_loss = the forward
+    wavefront of Scene.render_transparent + the ray_loss consumer (optim.py:96-106) over the valid paths  ->
+    loss.backward() = the backward kernel  ->  [N>1: NCCL all-reduce of grad_V].
+    (--unfused-loss: render_transparent + dense drt_ray_loss_grad + out_dir.backward instead.)  Views are sharded over ranks (view k -> rank k mod N), mesh/BVH replicated.
 
 `value`   : inputs resident in HBM, CUDA-event timed, max over ranks.
 `e2e`     : the same step through the public Scene API with HOST (pinned) ray buffers: per view
@@ -48,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-chain-gpu", action="store_true", help="skip the supplementary R-GPU baseline")
     ap.add_argument("--refit", action="store_true", help="refit instead of rebuilding the BVH each step")
+    ap.add_argument("--unfused-loss", action="store_true",
+                    help="ray loss as render_transparent + dense drt_ray_loss_grad + autograd instead of drt_b200.losses.ray_loss")
     return ap.parse_args()
 
 
@@ -181,7 +184,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import drt_b200.DiffRender as R
-    from drt_b200 import _lib, configs, dist as ddist, views
+    from drt_b200 import _lib, configs, dist as ddist, losses, views
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -233,6 +236,15 @@ def run_b200(args):
         if marks is not None: marks[0].record()
         scene.update_verticex(V)                                     # BVH rebuild
         if marks is not None: marks[1].record()
+        if not args.unfused_loss:
+            # public fused consumer (optim.py:91-108 as one autograd.Function): forward wavefront + loss over the
+            # valid records, then the backward kernel
+            loss = losses.ray_loss(scene, o, d, scr, val)
+            if marks is not None: marks[2].record(); marks[3].record()
+            loss.backward()
+            loss_buf.add_(loss.detach())
+            if marks is not None: marks[4].record()
+            return None
         out_ori, out_dir, mask = scene.render_transparent(o, d)      # fused forward kernel
         if marks is not None: marks[2].record()
         _lib.call("drt_ray_loss_grad", p(out_ori), p(out_dir), p(mask), p(scr), p(val), o.shape[0], p(gd), p(loss_buf),
@@ -249,15 +261,14 @@ def run_b200(args):
             torch.cuda.synchronize(dev)
 
     # ---- value: HBM-resident, K timed steps -------------------------------------------------
-    mask = None
     for _ in range(args.warmup):
         loss_buf.zero_()
-        mask = step(origin, ray_dir, screen, valid, g_dir)
+        step(origin, ray_dir, screen, valid, g_dir)
         if world > 1:
             ddist.allreduce_grad(V.grad)
     sync_all()
-    cov_hit = None
-    valid_frac = float(mask[:, 0].float().mean().item()) if n_local else 0.0
+    with torch.no_grad():
+        valid_frac = float(scene.render_transparent(origin, ray_dir)[2][:, 0].float().mean().item()) if n_local else 0.0
     sampler = ClockSampler(local)
     sampler.start()
     marks = [[ev() for _ in range(6)] for _ in range(args.steps)]
@@ -321,10 +332,15 @@ def run_b200(args):
                     ready[b].record(copy_stream)
                 main.wait_event(ready[b])
                 o, d, scr, val = bufs[b]
-                out_ori, out_dir, mask = scene.render_transparent(o, d)
-                _lib.call("drt_ray_loss_grad", p(out_ori), p(out_dir), p(mask), p(scr), p(val), n_pix, p(gds[b]), p(loss_buf),
-                          stream_ptr())
-                out_dir.backward(gds[b])
+                if not args.unfused_loss:
+                    view_loss = losses.ray_loss(scene, o, d, scr, val)
+                    view_loss.backward()
+                    loss_buf.add_(view_loss.detach())
+                else:
+                    out_ori, out_dir, mask = scene.render_transparent(o, d)
+                    _lib.call("drt_ray_loss_grad", p(out_ori), p(out_dir), p(mask), p(scr), p(val), n_pix, p(gds[b]), p(loss_buf),
+                              stream_ptr())
+                    out_dir.backward(gds[b])
                 free[b].record(main)
             if world > 1:
                 ddist.allreduce_grad(V.grad)

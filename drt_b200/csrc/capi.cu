@@ -447,4 +447,20 @@ int drt_ray_loss_grad(const double* out_ori, const double* out_dir, const uint8_
     return DRT_OK;
 }
 
+int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, const double* screen, const uint8_t* valid,
+                          const int32_t* rec, const int32_t* rec_count, int64_t N, double* g_out_dir, double* loss_sum, void* stream)
+{
+    if (N < 0) return fail(DRT_ERR_INVALID, "drt_ray_loss_grad_rec: N < 0");
+    if (N == 0) return DRT_OK;
+    if (!out_ori || !out_dir || !screen || !rec || !rec_count || !g_out_dir) return fail(DRT_ERR_INVALID, "drt_ray_loss_grad_rec: null buffer");
+    int dev = 0, sms = 148;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int grid = (int)std::min<int64_t>(blocks_for(N, 256), (int64_t)sms * 8);
+    ray_loss_rec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_ori, out_dir, screen, valid, (const int4*)rec, rec_count, g_out_dir, loss_sum);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
 }  // extern "C"

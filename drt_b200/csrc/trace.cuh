@@ -325,4 +325,38 @@ __global__ void __launch_bounds__(256) ray_loss_grad_kernel(const double* __rest
     }
 }
 
+// Same consumer, but driven by the compact records of the valid paths (7 % of the rays at C4) instead of a
+// pass over all N rays: g_out_dir rows of other rays are NOT touched (the backward kernel never reads them).
+__global__ void __launch_bounds__(256) ray_loss_rec_kernel(const double* __restrict__ out_ori,
+                                                           const double* __restrict__ out_dir,
+                                                           const double* __restrict__ screen,
+                                                           const uint8_t* __restrict__ valid, const int4* __restrict__ rec,
+                                                           const int* __restrict__ rec_count, double* __restrict__ g_dir,
+                                                           double* __restrict__ loss_sum)
+{
+    const int n = __ldg(rec_count);
+    double acc = 0.0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int64_t i = __ldg(rec + k).x;
+        d3 g = mk3(0, 0, 0);
+        if (!valid || valid[i]) {
+            d3 tg = ld3(screen + 3 * i) - ld3(out_ori + 3 * i);
+            tg = divs(tg, __dsqrt_rn(dot(tg, tg)));
+            d3 df = ld3(out_dir + 3 * i) - tg;
+            acc += dot(df, df);
+            g = df * 2.0;
+        }
+        st3(g_dir + 3 * i, g);
+    }
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    __shared__ double part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
+        if (loss_sum && s != 0.0) atomicAdd(loss_sum, s);
+    }
+}
+
 }  // namespace drt

@@ -1,6 +1,6 @@
 """Loss_calculator.ray_loss (reference optim.py:91-108) as one autograd.Function on the fused kernels
 (SURVEY.md 8(f) N2): forward = drt_trace_fwd + drt_ray_loss_grad (loss value and d loss/d out_dir in one
-pass over the rays), backward = drt_trace_bwd scaled by the upstream scalar.  out_ori is detached in
+pass over the valid paths), backward = drt_trace_bwd scaled by the upstream scalar.  out_ori is detached in
 the reference (optim.py:100), so only out_dir carries gradient."""
 import ctypes as C
 
@@ -39,8 +39,10 @@ class RayLoss(torch.autograd.Function):
         st = optix._stream_ptr(dev)
         _lib.call("drt_trace_fwd", mesh._h, _ptr(V), _ptr(o), _ptr(d), n, float(ext_ior), float(int_ior), _ptr(out_ori),
                   _ptr(out_dir), _ptr(mask), _ptr(rec), _ptr(rec_count), C.c_void_p(0), st)
-        _lib.call("drt_ray_loss_grad", _ptr(out_ori), _ptr(out_dir), _ptr(mask), _ptr(scr), _ptr(val), n, _ptr(g_dir),
-                  _ptr(loss), st)
+        # loss and d loss/d out_dir over the compact records of the valid paths only (rows of other rays stay
+        # unwritten: the backward kernel reads exactly the recorded rows)
+        _lib.call("drt_ray_loss_grad_rec", _ptr(out_ori), _ptr(out_dir), _ptr(scr), _ptr(val), _ptr(rec), _ptr(rec_count), n,
+                  _ptr(g_dir), _ptr(loss), st)
         ctx.mesh, ctx.iors = mesh, (float(ext_ior), float(int_ior))
         ctx.save_for_backward(V, o, d, rec, rec_count, g_dir)
         return loss[0]

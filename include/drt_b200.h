@@ -125,6 +125,15 @@ DRT_API int drt_trace_bwd(const drt_bvh* bvh, const double* V64, const double* o
 DRT_API int drt_ray_loss_grad(const double* out_ori, const double* out_dir, const uint8_t* mask3, const double* screen,
                       const uint8_t* valid, int64_t N, double* g_out_dir, double* loss_sum, void* stream);
 
+/*
+ * The same consumer driven by the compact hit records of drt_trace_fwd (one thread per VALID path instead of
+ * a pass over all N rays).  Only the g_out_dir rows of recorded rays are written -- exactly the rows
+ * drt_trace_bwd reads; N is the ray count the records were produced for (grid sizing only).
+ */
+DRT_API int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, const double* screen, const uint8_t* valid,
+                          const int32_t* rec, const int32_t* rec_count, int64_t N, double* g_out_dir, double* loss_sum,
+                          void* stream);
+
 /* Text of the last error on this thread ("" if none).  Never NULL. */
 DRT_API const char* drt_last_error(void);
 
