@@ -21,7 +21,10 @@
 
 namespace drt {
 
-constexpr int kFetchBatch = 64;
+#ifndef DRT_FETCH_BATCH
+#define DRT_FETCH_BATCH 64
+#endif
+constexpr int kFetchBatch = DRT_FETCH_BATCH;
 
 template <typename Dummy = void>
 __device__ __forceinline__ int warp_append(int* __restrict__ counter, bool pred)
