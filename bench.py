@@ -431,7 +431,8 @@ def run_b200(args):
             except Exception:
                 pass
             roof = {"bound": "hbm", "kernel": "fused forward = wf_q1+wf_r1+wf_q2+wf_r2+wf_q3 (one drt_trace_fwd call)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "peak_source": peak_src, "bytes_per_ray_fwd": b_fwd, "bytes_per_ray_total": b_tot,
+                    "traffic": traffic, "dram_gbs_actual": (traffic / (t_fwd_ms * 1e-3) / 1e9) if traffic else None,
+                    "peak_source": peak_src, "bytes_per_ray_fwd": b_fwd, "bytes_per_ray_total": b_tot,
                     "kernel_ms": t_fwd_ms, "rays_per_launch": n_total // world,
                     "step_frac": (b_tot * (n_total / world) / ((t_fwd_ms + t_bwd_ms) * 1e-3) / 1e9) / peak,
                     "model": "no-cache traversal bytes on the canonical LBVH (profiles/canonical_counters.json)"}

@@ -22,7 +22,7 @@
 namespace drt {
 
 #ifndef DRT_FETCH_BATCH
-#define DRT_FETCH_BATCH 64
+#define DRT_FETCH_BATCH 32
 #endif
 constexpr int kFetchBatch = DRT_FETCH_BATCH;
 
