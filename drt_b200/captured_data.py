@@ -1,0 +1,107 @@
+"""View-set loaders with the reference's `captured_data` interface.
+
+Schema of the captured sets (captured_data.py:94-108, 136-149): per object one file with
+`cam_proj [72,4,4]` (world->camera), `cam_k [3,3]`, `screen_position [72,N,3]` (measured 3-D screen point per
+pixel, zero where nothing was measured), `mask [72,resy,resx]` (uint8 silhouette), and for the Point Grey sets
+calibrated per-pixel `ray_origin/ray_dir [72,N,3]` (the Redmi sets derive rays from K and R, :149).
+The .h5 files themselves are not distributed (README.md:18) and h5py is not in this image, so the loader reads
+the same arrays from an .npz (or from an open h5py.File / any mapping when h5py is available) and keeps the
+72 views in pinned host memory exactly like the reference (:112-120).
+"""
+import numpy as np
+import torch
+
+from . import views as _views
+
+Float = torch.float64
+
+
+def process_mask(M):
+    """Soft silhouette mask in [0,1] from a binary one: signed 1-px Euclidean distance ramp across the
+    boundary, last row forced to 0.5 (captured_data.py:12-20; cv2.distanceTransform(DIST_L2, precise) ==
+    scipy's exact EDT)."""
+    from scipy.ndimage import distance_transform_edt as edt
+    M = np.asarray(M)
+    if M.max() == 255:
+        M = M // 255
+    assert M.max() == 1
+    dist = edt(M).clip(0, 1) - (edt(1 - M) - 1).clip(0, 1)
+    mask = (dist + 1) / 2
+    mask[-1] = 0.5
+    return mask
+
+
+def open_view_file(path):
+    """-> mapping with the schema above.  .npz always works; .h5 needs h5py."""
+    if str(path).endswith((".h5", ".hdf5")):
+        try:
+            import h5py
+        except ImportError as e:  # pragma: no cover - h5py is absent in this image
+            raise ImportError("reading the captured .h5 sets needs h5py; convert them to .npz with the same keys") from e
+        return h5py.File(path, "r")
+    return np.load(path)
+
+
+class Data:
+    """captured_data.Data (captured_data.py:43-82): get_view uploads one view; shuffled infinite generators."""
+
+    device = "cuda"
+
+    def get_view(self, V_index):
+        screen_pixel, valid, mask, origin, ray_dir, camera_M = self.Views[V_index]
+        up = lambda t: t.to(self.device, non_blocking=True)  # noqa: E731
+        return up(screen_pixel), up(valid), up(mask), up(origin), up(ray_dir), tuple(up(m) for m in camera_M)
+
+    def _cycle(self, index):
+        index = list(index)
+        while True:
+            np.random.shuffle(index)
+            for i in index:
+                yield int(i) % 72
+
+    def ray_view_generator(self):
+        index = list(np.arange(0, 72, 72 // self.num_view))
+        if self.name == "mouse":  # captured_data.py:66-68: the reference restricts the mouse to these views
+            index = list(np.arange(-5, 10)) + list(np.arange(22, 40))
+        return self._cycle(index)
+
+    def silh_view_generator(self):
+        return self._cycle(np.arange(72))
+
+    def _load(self, data, calibrated_rays):
+        pin = lambda a, dt=Float: torch.tensor(np.asarray(a), dtype=dt).pin_memory() if torch.cuda.is_available() \
+            else torch.tensor(np.asarray(a), dtype=dt)  # noqa: E731
+        K = np.asarray(data["cam_k"])
+        K_inv = np.linalg.inv(K)
+        self.Views = []
+        for i in range(len(data["cam_proj"])):
+            R = np.asarray(data["cam_proj"][i])
+            R_inv = np.linalg.inv(R)
+            screen = np.asarray(data["screen_position"][i]).reshape(-1, 3)
+            valid = screen[:, 0] != 0
+            mask = process_mask(np.asarray(data["mask"][i]))
+            if calibrated_rays:
+                origin, ray_dir = np.asarray(data["ray_origin"][i]), np.asarray(data["ray_dir"][i])
+            else:
+                o, d = _views.generate_ray(self.resy, self.resx, K_inv, R_inv)
+                origin, ray_dir = o.numpy(), d.numpy()
+            self.Views.append((pin(screen), pin(valid, torch.bool), pin(mask), pin(origin), pin(ray_dir),
+                               (pin(R), pin(K), pin(R_inv), pin(K_inv))))
+
+
+class Data_Pointgray(Data):
+    """960x1280 sets with calibrated per-pixel rays (hand, mouse, dog, monkey) -- captured_data.py:85-120."""
+
+    def __init__(self, HyperParams, path=None, data=None):
+        self.resy, self.resx = 960, 1280
+        self.num_view, self.name = HyperParams["num_view"], HyperParams["name"]
+        self._load(data if data is not None else open_view_file(path), calibrated_rays=True)
+
+
+class Data_Redmi(Data):
+    """1080x1920 pinhole sets (tiger, pig, horse, rabbit) -- captured_data.py:122-165."""
+
+    def __init__(self, HyperParams, path=None, data=None, res=(1080, 1920)):
+        self.resy, self.resx = res
+        self.num_view, self.name = HyperParams["num_view"], HyperParams["name"]
+        self._load(data if data is not None else open_view_file(path), calibrated_rays=False)

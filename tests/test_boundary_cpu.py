@@ -89,3 +89,37 @@ def test_generate_ray_convention():
     # pixel (x, y) -> row-major index y*resx + x; x grows to the right of the image
     px = (K @ (R[:3, :3] @ (o[0].numpy() + 5 * d[10].numpy()) + R[:3, 3]))
     assert np.allclose(px[:2] / px[2], [10, 0], atol=1e-9)
+
+
+def test_captured_data_loader_schema_and_soft_mask(tmp_path):
+    """N4: the captured-set schema (captured_data.py:94-108) read from an .npz stand-in; process_mask against
+    cv2's distance transform, which is what the reference calls (captured_data.py:12-20)."""
+    import cv2
+    from drt_b200 import captured_data as cd, meshgen, views
+    rng = np.random.default_rng(0)
+    M = np.zeros((40, 50), np.uint8)
+    cv2.circle(M, (25, 18), 11, 255, -1)
+    M[30:36, 5:20] = 255
+    m1 = M.copy() // 255
+    ref = (cv2.distanceTransform(m1, cv2.DIST_L2, 0) - 0).clip(0, 1) - (cv2.distanceTransform(1 - m1, cv2.DIST_L2, 0) - 1).clip(0, 1)
+    ref = (ref + 1) / 2
+    ref[-1] = 0.5
+    got = cd.process_mask(M)
+    assert got.shape == M.shape and np.abs(got - ref).max() < 1e-5 and got.min() == 0 and got.max() == 1
+    # a 3-view pinhole set, 12x16 pixels
+    v, _ = meshgen.icosahedron()
+    cams = views.turntable_cameras(v, 12, 16, 3)
+    screen = rng.normal(size=(3, 12 * 16, 3))
+    screen[:, ::5] = 0
+    masks = (rng.uniform(size=(3, 12, 16)) > 0.5).astype(np.uint8)
+    masks[:, 0, 0] = 1
+    p = str(tmp_path / "set.npz")
+    np.savez(p, cam_proj=np.stack([c[0] for c in cams]), cam_k=cams[0][1], screen_position=screen, mask=masks)
+    d = cd.Data_Redmi({"num_view": 3, "name": "horse"}, path=p, res=(12, 16))
+    d.device = "cpu"
+    assert len(d.Views) == 3
+    scr, valid, mask, origin, ray_dir, cam = d.get_view(1)
+    assert scr.shape == (192, 3) and valid.dtype == torch.bool and not valid[::5].any() and valid[1]
+    o_ref, d_ref = views.generate_ray(12, 16, cams[1][3], cams[1][2])
+    assert torch.allclose(ray_dir, d_ref) and torch.allclose(origin, o_ref) and mask.shape == (12, 16)
+    assert torch.allclose(cam[0] @ cam[2], torch.eye(4, dtype=torch.float64), atol=1e-12)
