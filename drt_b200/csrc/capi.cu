@@ -52,6 +52,7 @@ struct Tuning {
     bool simple_fwd = false;
     bool force_wavefront = false;
     bool one_launch = false;  // DRT_ONE_LAUNCH=1: the cooperative single-launch variant (measured 1.5 % slower: spills)
+    bool prefer_l1 = false;  // DRT_PREFER_L1=1 forces cudaSharedmemCarveoutMaxL1: measured 22 % SLOWER (the 1 KB/block reserve then caps residency at 4 blocks/SM)
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
     int thresh = 32;
     int minb = 8;
@@ -65,11 +66,13 @@ struct Tuning {
         if (t && atoi(t) >= 1 && atoi(t) <= 32) thresh = atoi(t);
         const char* ol = getenv("DRT_ONE_LAUNCH");
         if (ol && !strcmp(ol, "1")) one_launch = true;
+        const char* pl = getenv("DRT_PREFER_L1");
+        if (pl && !strcmp(pl, "1")) prefer_l1 = true;
         const char* z = getenv("DRT_BULK_ZERO");
         if (z && !strcmp(z, "0")) bulk = false;
         const char* m = getenv("DRT_Q_MINB");
         if (m) minb = atoi(m);
-        if (minb != 4 && minb != 6 && minb != 8 && minb != 10) minb = 8;
+        if (minb != 4 && minb != 6 && minb != 7 && minb != 8 && minb != 10) minb = 8;
     }
 };
 const Tuning& tuning()
@@ -254,6 +257,18 @@ int drt_bvh_create(int device, drt_bvh** out)
     CU(cudaMalloc(&b->scene, 8 * sizeof(unsigned)));
     CU(cudaMemset(b->scene, 0, 8 * sizeof(unsigned)));
     CU(cudaMalloc(&b->work, kWorkSlots * sizeof(unsigned long long)));
+    if (tuning().prefer_l1) {
+        // traversal kernels use < 1 KB of shared memory: ask for the largest L1 split explicitly
+        const int carve = cudaSharedmemCarveoutMaxL1;
+        CU(cudaFuncSetAttribute(wf_q1_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        CU(cudaFuncSetAttribute(wf_q2_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        CU(cudaFuncSetAttribute(wf_q3_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        CU(cudaFuncSetAttribute(wf_q1_kernel<7>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        CU(cudaFuncSetAttribute(wf_q2_kernel<7>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        CU(cudaFuncSetAttribute(wf_q3_kernel<7>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        CU(cudaFuncSetAttribute(closest_hit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        CU(cudaFuncSetAttribute(trace_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    }
     {
         int coop = 0;
         CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
@@ -396,6 +411,7 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
     do {                                                                                    \
         if (minb == 10) KERNEL<10><<<pg, 128, 0, st>>>(__VA_ARGS__);                        \
         else if (minb == 8) KERNEL<8><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
+        else if (minb == 7) KERNEL<7><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
         else if (minb == 6) KERNEL<6><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
         else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
     } while (0)
