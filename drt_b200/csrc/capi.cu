@@ -53,6 +53,7 @@ struct Tuning {
     bool force_wavefront = false;
     bool one_launch = false;  // DRT_ONE_LAUNCH=1: the cooperative single-launch variant (measured 1.5 % slower: spills)
     bool prefer_l1 = false;  // DRT_PREFER_L1=1 forces cudaSharedmemCarveoutMaxL1: measured 22 % SLOWER (the 1 KB/block reserve then caps residency at 4 blocks/SM)
+    int bwd_merge = -1;  // DRT_BWD_MERGE = 0 | 1 forces the run-merged backward scatter off / on (default: by rays per vertex)
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
     int thresh = 32;
     int minb = 8;
@@ -68,6 +69,8 @@ struct Tuning {
         if (ol && !strcmp(ol, "1")) one_launch = true;
         const char* pl = getenv("DRT_PREFER_L1");
         if (pl && !strcmp(pl, "1")) prefer_l1 = true;
+        const char* bm = getenv("DRT_BWD_MERGE");
+        if (bm && (!strcmp(bm, "0") || !strcmp(bm, "1"))) bwd_merge = atoi(bm);
         const char* z = getenv("DRT_BULK_ZERO");
         if (z && !strcmp(z, "0")) bulk = false;
         const char* m = getenv("DRT_Q_MINB");
@@ -441,8 +444,14 @@ int drt_trace_bwd(const drt_bvh* b, const double* V64, const double* origin, con
     if (!V64 || !origin || !dir || !rec || !rec_count || !g_out_dir || !grad_V) return fail(DRT_ERR_INVALID, "drt_trace_bwd: null buffer");
     DeviceGuard g(b->device);
     int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
-    trace_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, ext_ior, int_ior, (const int4*)rec,
-                                                              rec_count, g_out_ori, g_out_dir, grad_V);
+    // many rays per vertex = heavy contention on the float64 atomics: merge equal-triangle runs in the warp first
+    const bool merge = tuning().bwd_merge == 1 || (tuning().bwd_merge < 0 && N / std::max(b->nV, 1) > 5000);
+    if (merge)
+        trace_bwd_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, ext_ior, int_ior, (const int4*)rec,
+                                                                    rec_count, g_out_ori, g_out_dir, grad_V);
+    else
+        trace_bwd_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, ext_ior, int_ior, (const int4*)rec,
+                                                                     rec_count, g_out_ori, g_out_dir, grad_V);
     ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;

@@ -236,15 +236,18 @@ def test_wavefront_path_large_batch_vs_oracle(cuda_device):
     assert np.array_equal(hm > 0, q["stage"] >= 1)
 
 
-@pytest.mark.parametrize("kernel", ["wavefront", "simple", "onelaunch"])
+@pytest.mark.parametrize("kernel", ["wavefront", "simple", "onelaunch", "bwd-merge", "bwd-nomerge"])
 def test_every_forward_kernel_variant_passes_the_parity_suite(kernel):
     """The kernel choice is by batch size; force each variant (five-launch wavefront, one-thread-per-path
     megakernel, cooperative single-launch wavefront) over the whole golden/oracle suite."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, DRT_FWD_KERNEL="wavefront" if kernel == "onelaunch" else kernel,
-               DRT_ONE_LAUNCH="1" if kernel == "onelaunch" else "0")
+    env = dict(os.environ, DRT_ONE_LAUNCH="1" if kernel == "onelaunch" else "0")
+    if kernel in ("wavefront", "simple", "onelaunch"):
+        env["DRT_FWD_KERNEL"] = "wavefront" if kernel == "onelaunch" else kernel
+    else:  # both variants of the backward scatter (the default picks one by rays per vertex)
+        env["DRT_BWD_MERGE"] = "1" if kernel == "bwd-merge" else "0"
     if os.environ.get("DRT_PARITY_CHILD"):
         pytest.skip("already inside the forced-kernel child run")
     env["DRT_PARITY_CHILD"] = "1"
