@@ -4,14 +4,20 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config C4] [--impl reference]
 
 A step = one optim.py-shaped ray iteration over the whole view set of the config:
-    Scene.update_verticex (BVH rebuild, DiffRender.py:378-380)  ->  drt_b200.losses.ray_loss = the forward
-    wavefront of Scene.render_transparent + the ray_loss consumer (optim.py:96-106) over the valid paths  ->
-    loss.backward() = the backward kernel  ->  [N>1: NCCL all-reduce of grad_V].
-    (--unfused-loss: render_transparent + dense drt_ray_loss_grad + out_dir.backward instead.)  Views are sharded over ranks (view k -> rank k mod N), mesh/BVH replicated.
+    Scene.update_verticex (BVH rebuild, DiffRender.py:378-380)  ->  drt_b200.losses.ray_loss =
+    drt_ray_loss_step: the forward wavefront of Scene.render_transparent, the ray_loss consumer
+    (optim.py:96-106) and the analytic backward over the valid paths, six launches, no dense per-ray
+    output  ->  loss.backward() (scales the gradient)  ->  [N>1: NCCL all-reduce of grad_V].
+    --loss-path rec   : the earlier three-call route (drt_trace_fwd -> drt_ray_loss_grad_rec -> drt_trace_bwd)
+    --loss-path dense : render_transparent + dense drt_ray_loss_grad + out_dir.backward
+    Views are sharded over ranks (view k -> rank k mod N), mesh/BVH replicated.
 
 `value`   : inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e`     : the same step through the public Scene API with HOST (pinned) ray buffers: per view
-            H2D of origin/ray_dir/screen/valid, D2H of grad_V + loss, copies inside the timed region.
+`e2e`     : the same step through the public API (losses.ray_loss_view) with HOST (pinned) view buffers in
+            the loader's lossless compact form (captured_data.CompactView: one origin per pinhole view,
+            ray_dir, the measured screen points only), per view H2D, D2H of grad_V + loss, copies inside
+            the timed region.  `e2e_reference_layout`: the same with the reference's dense per-view tensors
+            (origin/ray_dir/screen_pixel f64 [N,3] + valid, 73 B per ray: captured_data.py:112-120).
 `roofline`: dominant kernel (fused forward) -- algorithmic bytes (profiles/canonical_counters.json,
             frozen from the CPU oracle's canonical-LBVH counters) / CUDA-event kernel time, against
             MEASURED_PEAKS.json's HBM copy bandwidth.
@@ -49,8 +55,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-chain-gpu", action="store_true", help="skip the supplementary R-GPU baseline")
     ap.add_argument("--refit", action="store_true", help="refit instead of rebuilding the BVH each step")
-    ap.add_argument("--unfused-loss", action="store_true",
-                    help="ray loss as render_transparent + dense drt_ray_loss_grad + autograd instead of drt_b200.losses.ray_loss")
+    ap.add_argument("--loss-path", default="step", choices=["step", "rec", "dense"],
+                    help="step: drt_ray_loss_step (default); rec: three-call route; dense: render_transparent + dense loss")
+    ap.add_argument("--unfused-loss", action="store_true", help="same as --loss-path dense")
     return ap.parse_args()
 
 
@@ -197,6 +204,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
+    if args.unfused_loss:
+        args.loss_path = "dense"
     cfg = configs.make(args.config)
     if args.views:
         cfg["cams"] = cfg["cams"][:args.views]
@@ -222,7 +231,10 @@ def run_b200(args):
         screen = (t_ori + 100.0 * t_dir).contiguous()      # a measured 3-D screen point per pixel (optim.py:96)
         valid = t_mask[:, 0].contiguous()
     del tgt_scene, t_ori, t_dir, t_mask
-    g_dir = torch.empty_like(origin)
+    # resident inputs of the fused step: one origin row per view, ray_dir, the measured screen points only
+    origins = torch.stack([origin[j * n_pix] for j in range(len(cams))]) if cams else origin[:0]
+    sparse = losses.SparseTargets.from_dense(screen, valid)
+    g_dir = torch.empty_like(origin) if args.loss_path == "dense" else None
     loss_buf = torch.zeros(1, dtype=torch.float64, device=dev)
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
     stream_ptr = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)  # noqa: E731
@@ -236,10 +248,17 @@ def run_b200(args):
         if marks is not None: marks[0].record()
         scene.update_verticex(V)                                     # BVH rebuild
         if marks is not None: marks[1].record()
-        if not args.unfused_loss:
-            # public fused consumer (optim.py:91-108 as one autograd.Function): forward wavefront + loss over the
-            # valid records, then the backward kernel
-            loss = losses.ray_loss(scene, o, d, scr, val)
+        if args.loss_path == "step":
+            # public fused consumer (optim.py:91-108 + :210 as one autograd.Function = one library call): forward
+            # wavefront, then loss + analytic backward over the valid paths; the library records marks[2] between them
+            loss = losses.ray_loss(scene, origins, d, targets=sparse, ev_after_fwd=marks[2].cuda_event if marks is not None else None)
+            if marks is not None: marks[3].record()
+            loss.backward()
+            loss_buf.add_(loss.detach())
+            if marks is not None: marks[4].record()
+            return None
+        if args.loss_path == "rec":
+            loss = losses.ray_loss_rec(scene, o, d, scr, val)
             if marks is not None: marks[2].record(); marks[3].record()
             loss.backward()
             loss_buf.add_(loss.detach())
@@ -272,6 +291,8 @@ def run_b200(args):
     sampler = ClockSampler(local)
     sampler.start()
     marks = [[ev() for _ in range(6)] for _ in range(args.steps)]
+    for m in marks:
+        m[2].record()  # creates the cudaEvent_t the library re-records between forward and loss/backward
     launches0 = lib.drt_kernel_launches()
     sync_all()
     sampler.active = True
@@ -294,6 +315,9 @@ def run_b200(args):
     sync_all()
     t_total_ms = start.elapsed_time(end)
     phases = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / args.steps for i in range(5)]
+    if args.loss_path == "step":  # marks[2] = end of the forward wavefront (recorded by the library), marks[4] = end of backward
+        phases[3] = phases[2] + phases[3]
+        phases[2] = 0.0
     tt = torch.tensor([t_total_ms, phases[1], phases[3], phases[0], phases[4]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -304,71 +328,133 @@ def run_b200(args):
     grad_norm = float(V.grad.norm().item())
 
     # ---- e2e: host buffers, copies inside the timed region ----------------------------------
-    e2e = None
+    e2e = e2e_ref_layout = None
     if not args.no_e2e:
+        from drt_b200.captured_data import CompactView
         host = [t.cpu().pin_memory() for t in (origin, ray_dir, screen, valid)]
-        del origin, ray_dir, screen, valid, g_dir
+        del origin, ray_dir, screen, valid, g_dir, sparse
         torch.cuda.empty_cache()
         nbuf = 2
-        bufs = [[torch.empty((n_pix,) + h.shape[1:], dtype=h.dtype, device=dev) for h in host] for _ in range(nbuf)]
-        gds = [torch.empty((n_pix, 3), dtype=torch.float64, device=dev) for _ in range(nbuf)]
         copy_stream = torch.cuda.Stream(dev)
         ready = [torch.cuda.Event() for _ in range(nbuf)]
         free = [torch.cuda.Event() for _ in range(nbuf)]
         grad_host = torch.empty((nV, 3), dtype=torch.float64).pin_memory()
         loss_host = torch.empty(1, dtype=torch.float64).pin_memory()
         main = torch.cuda.current_stream(dev)
+        view_slice = lambda t, j: t[j * n_pix:(j + 1) * n_pix]  # noqa: E731
 
-        def e2e_step():
-            V.grad = None
-            loss_buf.zero_()
-            scene.update_verticex(V)
-            for j in range(len(cams)):
-                b = j % nbuf
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(free[b])            # the compute that last used this buffer is done
-                    for dst, src in zip(bufs[b], host):
-                        dst.copy_(src[j * n_pix:(j + 1) * n_pix], non_blocking=True)
-                    ready[b].record(copy_stream)
-                main.wait_event(ready[b])
+        def make_reference_layout():
+            """the reference's per-view tensors (captured_data.py:112-120): origin, ray_dir, screen_pixel f64 [N,3] + valid"""
+            bufs = [[torch.empty((n_pix,) + h.shape[1:], dtype=h.dtype, device=dev) for h in host] for _ in range(nbuf)]
+            gds = [torch.empty((n_pix, 3), dtype=torch.float64, device=dev) for _ in range(nbuf)] if args.loss_path == "dense" else None
+
+            def upload(j, b):
+                for dst, src in zip(bufs[b], host):
+                    dst.copy_(view_slice(src, j), non_blocking=True)
+
+            def compute(j, b):
                 o, d, scr, val = bufs[b]
-                if not args.unfused_loss:
-                    view_loss = losses.ray_loss(scene, o, d, scr, val)
-                    view_loss.backward()
-                    loss_buf.add_(view_loss.detach())
-                else:
-                    out_ori, out_dir, mask = scene.render_transparent(o, d)
-                    _lib.call("drt_ray_loss_grad", p(out_ori), p(out_dir), p(mask), p(scr), p(val), n_pix, p(gds[b]), p(loss_buf),
-                              stream_ptr())
-                    out_dir.backward(gds[b])
-                free[b].record(main)
-            if world > 1:
-                ddist.allreduce_grad(V.grad)
-            grad_host.copy_(V.grad, non_blocking=True)
-            loss_host.copy_(loss_buf, non_blocking=True)
-            main.synchronize()                                  # the result is on the host
+                if args.loss_path == "step":
+                    return losses.ray_loss(scene, o, d, screen=scr, valid=val)
+                if args.loss_path == "rec":
+                    return losses.ray_loss_rec(scene, o, d, scr, val)
+                out_ori, out_dir, mask = scene.render_transparent(o, d)
+                _lib.call("drt_ray_loss_grad", p(out_ori), p(out_dir), p(mask), p(scr), p(val), n_pix, p(gds[b]), p(loss_buf),
+                          stream_ptr())
+                out_dir.backward(gds[b])
+                return None
+            return upload, compute, int(n_total * (24 + 24 + 24 + 1))
 
-        for b in range(nbuf):
-            free[b].record(main)
-        for _ in range(max(1, min(args.warmup, 3))):
-            e2e_step()
-        sync_all()
-        k_e2e = max(3, min(args.steps, 10))
-        s2, e2 = ev(), ev()
-        s2.record()
-        for _ in range(k_e2e):
-            e2e_step()
-        e2.record()
-        torch.cuda.synchronize(dev)
-        te = torch.tensor([s2.elapsed_time(e2)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_ms = te.item() / k_e2e
-        e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": k_e2e,
-               "h2d_bytes_per_step": int(n_total * (24 + 24 + 24 + 1)), "d2h_bytes_per_step": int(world * (nV * 24 + 8)),
-               "note": "per-view H2D of origin/ray_dir/screen/valid from pinned host memory, double-buffered on a copy stream; "
-                       "D2H of grad_V and loss; through Scene.update_verticex/render_transparent/backward"}
-        assert abs(loss_host.item() - loss_val) <= 1e-6 * max(1.0, abs(loss_val)), (loss_host.item(), loss_val)
+        def make_compact_layout():
+            """the loader's lossless compact form (captured_data.CompactView): one origin row per pinhole view, ray_dir,
+            sorted indices + screen points of the measured pixels only"""
+            cvs = [CompactView.from_reference_view((view_slice(host[2], j), view_slice(host[3], j), None, view_slice(host[0], j),
+                                                    view_slice(host[1], j), None)).pin_memory() for j in range(len(cams))]
+            max_t = max([len(c.targets) for c in cvs] + [1])
+            rows = max([c.origin.shape[0] for c in cvs] + [1])
+            bufs = [dict(o=torch.empty((rows, 3), dtype=torch.float64, device=dev), d=torch.empty((n_pix, 3), dtype=torch.float64, device=dev),
+                         idx=torch.empty(max_t, dtype=torch.int32, device=dev), xyz=torch.empty((max_t, 3), dtype=torch.float64, device=dev))
+                    for _ in range(nbuf)]
+
+            def upload(j, b):
+                c, B = cvs[j], bufs[b]
+                nt, r = len(c.targets), c.origin.shape[0]
+                B["o"][:r].copy_(c.origin, non_blocking=True)
+                B["d"].copy_(c.ray_dir, non_blocking=True)
+                B["idx"][:nt].copy_(c.targets.idx, non_blocking=True)
+                B["xyz"][:nt].copy_(c.targets.xyz, non_blocking=True)
+
+            def compute(j, b):
+                c, B = cvs[j], bufs[b]
+                nt, r = len(c.targets), c.origin.shape[0]
+                return losses.ray_loss_view(scene, CompactView(B["o"][:r], B["d"], losses.SparseTargets(B["idx"][:nt], B["xyz"][:nt])))
+            h2d = sum(c.h2d_bytes() for c in cvs)
+            if world > 1:
+                t = torch.tensor([h2d], dtype=torch.float64, device=dev)
+                dist.all_reduce(t)
+                h2d = t.item()
+            return upload, compute, int(h2d)
+
+        def time_e2e(upload, compute):
+            def e2e_step():
+                V.grad = None
+                loss_buf.zero_()
+                scene.update_verticex(V)
+                for j in range(len(cams)):
+                    b = j % nbuf
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(free[b])            # the compute that last used this buffer is done
+                        upload(j, b)
+                        ready[b].record(copy_stream)
+                    main.wait_event(ready[b])
+                    view_loss = compute(j, b)
+                    if view_loss is not None:
+                        view_loss.backward()
+                        loss_buf.add_(view_loss.detach())
+                    free[b].record(main)
+                if world > 1:
+                    ddist.allreduce_grad(V.grad)
+                grad_host.copy_(V.grad, non_blocking=True)
+                loss_host.copy_(loss_buf, non_blocking=True)
+                main.synchronize()                                  # the result is on the host
+
+            for b in range(nbuf):
+                free[b].record(main)
+            for _ in range(max(1, min(args.warmup, 3))):
+                e2e_step()
+            sync_all()
+            k_e2e = max(3, min(args.steps, 10))
+            s2, e2 = ev(), ev()
+            s2.record()
+            for _ in range(k_e2e):
+                e2e_step()
+            e2.record()
+            torch.cuda.synchronize(dev)
+            te = torch.tensor([s2.elapsed_time(e2)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            assert abs(loss_host.item() - loss_val) <= 1e-6 * max(1.0, abs(loss_val)), (loss_host.item(), loss_val)
+            return te.item() / k_e2e, k_e2e
+
+        d2h = int(world * (nV * 24 + 8))
+        up, comp, h2d = make_reference_layout()
+        ms, k_e2e = time_e2e(up, comp)
+        e2e_ref_layout = {"value": n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": k_e2e, "h2d_bytes_per_step": h2d,
+                          "d2h_bytes_per_step": d2h,
+                          "note": "per-view H2D of the reference's dense view tensors (origin/ray_dir/screen_pixel f64 [N,3] + valid, "
+                                  "73 B per ray) from pinned host memory, double-buffered on a copy stream; D2H of grad_V and loss"}
+        del up, comp
+        torch.cuda.empty_cache()
+        if args.loss_path == "step":
+            up, comp, h2d = make_compact_layout()
+            ms, k_e2e = time_e2e(up, comp)
+            e2e = {"value": n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": k_e2e, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h,
+                   "note": "per-view H2D from pinned host memory of the loader's lossless compact view (captured_data.CompactView: "
+                           "one origin row per pinhole view, ray_dir f64 [N,3], int32 index + f64 screen point of the measured pixels "
+                           "only), double-buffered on a copy stream; losses.ray_loss_view per view; D2H of grad_V and loss"}
+        else:
+            e2e, e2e_ref_layout = e2e_ref_layout, None
     sampler.stop()
 
     # ---- R-GPU (supplementary, rank 0, N=1 only): the reference's approach on this same B200 --------------
@@ -426,11 +512,11 @@ def run_b200(args):
             ach = b_fwd * (n_total / world) / (t_fwd_ms * 1e-3) / 1e9
             traffic = None
             try:
-                per_ray = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["trace_fwd"]["dram_bytes_per_ray"]
+                per_ray = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["loss_step_fwd" if args.loss_path == "step" else "trace_fwd"]["dram_bytes_per_ray"]
                 traffic = per_ray * (n_total / world)  # ncu --set full capture, scaled to this launch's ray count
             except Exception:
                 pass
-            roof = {"bound": "hbm", "kernel": "fused forward = wf_q1+wf_r1+wf_q2+wf_r2+wf_q3 (one drt_trace_fwd call)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            roof = {"bound": "hbm", "kernel": ("forward wavefront = ls_q1+ls_r1+ls_q2+ls_r2+ls_q3 (first five launches of drt_ray_loss_step)" if args.loss_path == "step" else "fused forward = wf_q1+wf_r1+wf_q2+wf_r2+wf_q3 (one drt_trace_fwd call)"), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "dram_gbs_actual": (traffic / (t_fwd_ms * 1e-3) / 1e9) if traffic else None,
                     "peak_source": peak_src, "bytes_per_ray_fwd": b_fwd, "bytes_per_ray_total": b_tot,
                     "kernel_ms": t_fwd_ms, "rays_per_launch": n_total // world,
@@ -442,12 +528,12 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": workload_name(cfg, n_views), "rays_per_step": n_total, "views_per_gpu": len(cams),
                        "parallelism": f"views sharded over {world} GPU(s), mesh/BVH replicated, 1 all-reduce of grad_V",
-                       "bvh": "refit each step" if args.refit else "full LBVH rebuild each step",
+                       "bvh": "refit each step" if args.refit else "full LBVH rebuild each step", "loss_path": args.loss_path,
                        "l2": "inputs larger than L2 (%.1f GB of rays per step per GPU)" % (n_local * 48 / 1e9),
                        "int_ior": configs.INT_IOR, "valid_frac_rank0": valid_frac},
             "phases_ms": {"bvh_build": t_build_ms, "fwd": t_fwd_ms, "loss_grad": phases[2], "bwd": t_bwd_ms, "allreduce": t_ar_ms},
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
-            "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "e2e": e2e, "e2e_reference_layout": e2e_ref_layout, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "loss": loss_val, "grad_norm": grad_norm,
         }
         print(json.dumps(out), flush=True)

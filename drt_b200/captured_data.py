@@ -42,7 +42,55 @@ def open_view_file(path):
     return np.load(path)
 
 
-class Data:
+class CompactView:
+    """One view in the lossless compact form the fused ray-loss step consumes (drt_b200.losses.ray_loss_view):
+    `origin` [1,3] when every ray of the view starts at the same point (a pinhole view: captured_data.py:38
+    expands ONE camera centre to [N,3]) else [N,3]; `ray_dir` [N,3]; `targets` = SparseTargets of the measured
+    pixels (captured_data.py:104: valid = screen_pixel[:,0] != 0).  73 B per ray of the reference layout become
+    24 B + 28 B per MEASURED pixel; nothing is rounded."""
+
+    __slots__ = ("origin", "ray_dir", "targets", "mask", "camera_M")
+
+    def __init__(self, origin, ray_dir, targets, mask=None, camera_M=None):
+        self.origin, self.ray_dir, self.targets, self.mask, self.camera_M = origin, ray_dir, targets, mask, camera_M
+
+    @staticmethod
+    def from_reference_view(view):
+        """(screen_pixel, valid, mask, origin, ray_dir, camera_M) as captured_data.Data.Views holds it -> CompactView."""
+        from .losses import SparseTargets
+        screen, valid, mask, origin, ray_dir, cam = view
+        one = origin.shape[0] > 0 and bool((origin == origin[:1]).all())
+        return CompactView(origin[:1].clone() if one else origin, ray_dir, SparseTargets.from_dense(screen, valid), mask, cam)
+
+    def pin_memory(self):
+        pin = lambda t: t.pin_memory() if torch.cuda.is_available() else t  # noqa: E731
+        return CompactView(pin(self.origin), pin(self.ray_dir), self.targets.pin_memory() if torch.cuda.is_available()
+                           else self.targets, self.mask, self.camera_M)
+
+    def to(self, device, non_blocking=True):
+        up = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)  # noqa: E731
+        cam = None if self.camera_M is None else tuple(up(m) for m in self.camera_M)
+        return CompactView(up(self.origin), up(self.ray_dir), self.targets.to(device, non_blocking), up(self.mask), cam)
+
+    def h2d_bytes(self):
+        """bytes the ray path needs on the device (mask / camera_M belong to the silhouette path)"""
+        return sum(t.numel() * t.element_size() for t in (self.origin, self.ray_dir, self.targets.idx, self.targets.xyz))
+
+
+class CompactViews:
+    """Mixin for the loaders: compact pinned host copies built once per view, uploaded per iteration."""
+
+    def compact(self, V_index):
+        cache = self.__dict__.setdefault("_compact", {})
+        if V_index not in cache:
+            cache[V_index] = CompactView.from_reference_view(self.Views[V_index]).pin_memory()
+        return cache[V_index]
+
+    def get_view_compact(self, V_index):
+        return self.compact(V_index).to(self.device)
+
+
+class Data(CompactViews):
     """captured_data.Data (captured_data.py:43-82): get_view uploads one view; shuffled infinite generators."""
 
     device = "cuda"

@@ -5,7 +5,7 @@
 #include <cstring>
 
 #include "../../include/drt_b200.h"
-#include "wavefront.cuh"
+#include "loss_step.cuh"
 
 using namespace drt;
 
@@ -106,6 +106,9 @@ struct drt_bvh {
     unsigned* scene = nullptr;                   // 6 encoded floats + 1 int (bad index count) + pad
     int4* listA = nullptr;     size_t capLA = 0; // wavefront list L (ray, tri1, tri2, dead) of the rays that hit
     int4* listB = nullptr;     size_t capLB = 0; // wavefront list M: entries of L that survive both refractions
+    double* park = nullptr;    size_t capPk = 0; // loss step: parked rays, 6 component columns of capPk/6 slots
+    int* listM = nullptr;      size_t capLM = 0; // loss step: slots of L that survive both refractions
+    int* listS = nullptr;      size_t capLS = 0; // loss step: slots of L whose exit ray is unoccluded (the valid paths)
     unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
     int work_slot = 0;
     int fused_blocks_per_sm = 0;                 // co-resident blocks of wf_fused_kernel<8> (0: no cooperative launch)
@@ -237,7 +240,7 @@ int build_common(drt_bvh* b, const int32_t* F, int nF, const float* V32, const d
 
 extern "C" {
 
-int drt_version(void) { return 1000; }
+int drt_version(void) { return 1001; }
 
 unsigned long long drt_kernel_launches(void) { return g_launches; }
 
@@ -288,7 +291,7 @@ int drt_bvh_destroy(drt_bvh* b)
     if (!b) return DRT_OK;
     DeviceGuard g(b->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {b->listA, b->listB, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
+    void* ptrs[] = {b->listA, b->listB, b->park, b->listM, b->listS, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -484,6 +487,92 @@ int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, const do
     int grid = (int)std::min<int64_t>(blocks_for(N, 256), (int64_t)sms * 8);
     ray_loss_rec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_ori, out_dir, screen, valid, (const int4*)rec, rec_count, g_out_dir, loss_sum);
     ++g_launches;
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin, int64_t rays_per_origin, const double* dir,
+                      int64_t N, double ext_ior, double int_ior, int target_mode, const double* screen, const uint8_t* valid,
+                      const int32_t* tgt_idx, const double* tgt_xyz, int64_t n_tgt, double* loss_sum, double* grad_V,
+                      int32_t* n_paths, void* ev_after_fwd, void* stream)
+{
+    drt_bvh* b = const_cast<drt_bvh*>(b_);
+    if (!b) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: null handle");
+    if (!b->built) return fail(DRT_ERR_STATE, "drt_ray_loss_step: no mesh has been set (update_mesh first)");
+    if (N < 0 || N > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: N must be in [0, 2^31)");
+    if (rays_per_origin < 1 || rays_per_origin > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: rays_per_origin must be >= 1");
+    if (target_mode != 0 && target_mode != 1) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: target_mode must be 0 (dense) or 1 (sparse)");
+    if (n_tgt < 0 || n_tgt > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: n_tgt must be in [0, 2^31)");
+    DeviceGuard g(b->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_paths) CU(cudaMemsetAsync(n_paths, 0, sizeof(int32_t), st));
+    if (N == 0 || b->nF == 0) {
+        if (ev_after_fwd) CU(cudaEventRecord((cudaEvent_t)ev_after_fwd, st));
+        return DRT_OK;
+    }
+    if (!V64 || !origin || !dir || !loss_sum) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: null buffer");
+    if (target_mode == 0 && !screen) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: dense targets need screen[N,3]");
+    if (target_mode == 1 && n_tgt > 0 && (!tgt_idx || !tgt_xyz)) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: sparse targets need tgt_idx and tgt_xyz");
+    int rc;
+    if ((rc = ensure(b->listA, b->capLA, (size_t)N))) return rc;
+    if ((rc = ensure(b->park, b->capPk, 6 * (size_t)N))) return rc;
+    if ((rc = ensure(b->listM, b->capLM, (size_t)N))) return rc;
+    if ((rc = ensure(b->listS, b->capLS, (size_t)N))) return rc;
+    // control block: work counters of Q1,Q2,Q3 + {countL, countM} + {countS, -}
+    unsigned long long* ctl = b->work + (size_t)(b->work_slot++ % (kWorkSlots / 8)) * 8;
+    CU(cudaMemsetAsync(ctl, 0, 8 * sizeof(unsigned long long), st));
+    int* countL = (int*)(ctl + 3);
+    int* countM = countL + 1;
+    int* countS = (int*)(ctl + 4);
+    const int thresh = tuning().thresh;
+    const int minb = tuning().minb;
+    const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
+    const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
+    const RaySrc rays{origin, dir, (int)rays_per_origin};
+    const Park park{b->park, (int64_t)(b->capPk / 6)};
+    const TargetSrc tgt{screen, valid, tgt_idx, tgt_xyz, (int)n_tgt, target_mode};
+#define DRT_LAUNCH_Q(KERNEL, ...)                                                           \
+    do {                                                                                    \
+        if (minb == 10) KERNEL<10><<<pg, 128, 0, st>>>(__VA_ARGS__);                        \
+        else if (minb == 8) KERNEL<8><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
+        else if (minb == 7) KERNEL<7><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
+        else if (minb == 6) KERNEL<6><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
+        else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
+    } while (0)
+    LossEntryJob j1{rays, b->listA, countL};
+    DRT_LAUNCH_Q(ls_q1_kernel, b->view(), j1, (int)N, ctl + 0, thresh);
+    ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park);
+    LossExitJob j2{park, b->listA};
+    DRT_LAUNCH_Q(ls_q2_kernel, b->view(), j2, countL, ctl + 1, thresh);
+    ls_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, b->listA, countL, park, b->listM, countM);
+    LossOcclusionJob j3{park, b->listM, b->listS, countS};
+    DRT_LAUNCH_Q(ls_q3_kernel, b->view(), j3, countM, ctl + 2, thresh);
+#undef DRT_LAUNCH_Q
+    if (ev_after_fwd) CU(cudaEventRecord((cudaEvent_t)ev_after_fwd, st));
+    const bool merge = tuning().bwd_merge == 1 || (tuning().bwd_merge < 0 && N / std::max(b->nV, 1) > 5000);
+    if (!grad_V)
+        ls_loss_bwd_kernel<false, false><<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, nullptr);
+    else if (merge)
+        ls_loss_bwd_kernel<true, true><<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
+    else
+        ls_loss_bwd_kernel<true, false><<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
+    g_launches += 6;
+    CU(cudaGetLastError());
+    if (n_paths) CU(cudaMemcpyAsync(n_paths, countS, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return DRT_OK;
+}
+
+int drt_generate_rays(int32_t resy, int32_t resx, const double* K_inverse, const double* R_inverse, double* origin3, double* dir,
+                      void* stream)
+{
+    if (resy < 0 || resx < 0 || (int64_t)resy * resx > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_generate_rays: bad resolution %d x %d", resy, resx);
+    if (!K_inverse || !R_inverse || !origin3 || (!dir && (int64_t)resy * resx > 0)) return fail(DRT_ERR_INVALID, "drt_generate_rays: null buffer");
+    int dev = 0, sms = 148;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t n = (int64_t)resy * resx;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_for(n, 256), (int64_t)sms * 16));
+    generate_rays_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(resy, resx, K_inverse, R_inverse, origin3, dir); ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
 }

@@ -1,7 +1,15 @@
 """Loss_calculator.ray_loss (reference optim.py:91-108) as one autograd.Function on the fused kernels
-(SURVEY.md 8(f) N2): forward = drt_trace_fwd + drt_ray_loss_grad (loss value and d loss/d out_dir in one
-pass over the valid paths), backward = drt_trace_bwd scaled by the upstream scalar.  out_ori is detached in
-the reference (optim.py:100), so only out_dir carries gradient."""
+(SURVEY.md 8(f) N2).  out_ori is detached in the reference (optim.py:100), so only out_dir carries gradient.
+
+`ray_loss` / `ray_loss_view` = drt_ray_loss_step: the forward wavefront, the loss and the vertex gradient in ONE
+library call with no dense per-ray output at all (rays that miss write nothing, d loss/d out_dir is never
+stored); the gradient is computed together with the loss and scaled by the upstream scalar in backward().
+The ray origin may be one row per ray (the reference layout), an expanded / single-row tensor (a pinhole view
+has ONE origin, captured_data.py:38) or one row per view; the screen targets may be the reference's dense
+(screen_pixel, valid) pair or `SparseTargets` (only the measured pixels, captured_data.py:104).
+
+`ray_loss_rec` = the earlier three-call route (drt_trace_fwd -> drt_ray_loss_grad_rec -> drt_trace_bwd), kept
+for A/B measurements: it still materialises out_ori / out_dir / mask / d loss/d out_dir."""
 import ctypes as C
 
 import torch
@@ -57,6 +65,118 @@ class RayLoss(torch.autograd.Function):
         return grad_V * g_loss, None, None, None, None, None, None, None
 
 
-def ray_loss(scene, origin, ray_dir, screen, valid=None):
-    """sum over valid & traced rays of || out_dir - normalize(screen - out_ori) ||^2  (optim.py:96-106)."""
+def ray_loss_rec(scene, origin, ray_dir, screen, valid=None):
+    """The three-call route (dense out_ori/out_dir/mask and d loss/d out_dir in memory); same value and gradient."""
     return RayLoss.apply(scene.vertices, origin, ray_dir, screen, valid, scene.optix_mesh, _R.intIOR, _R.extIOR)
+
+
+class SparseTargets:
+    """Screen targets of the measured pixels only: `idx` int32 [n] ray indices, strictly ascending, `xyz` float64
+    [n,3] screen points.  Equivalent to the reference's dense pair with valid = False everywhere else
+    (captured_data.py:101-104: valid = screen_pixel[:,0] != 0)."""
+
+    def __init__(self, idx, xyz):
+        if idx.dtype != torch.int32 or idx.dim() != 1:
+            raise TypeError("SparseTargets.idx must be int32 [n]")
+        if xyz.dtype != torch.float64 or xyz.shape != (idx.shape[0], 3):
+            raise TypeError("SparseTargets.xyz must be float64 [n,3]")
+        self.idx, self.xyz = idx.contiguous(), xyz.contiguous()
+
+    @staticmethod
+    def from_dense(screen, valid=None):
+        """valid rows of a dense (screen_pixel [N,3], valid [N]) pair -> SparseTargets on the same device."""
+        if valid is None:
+            valid = screen[:, 0] != 0  # captured_data.py:104
+        idx = torch.nonzero(valid, as_tuple=False).reshape(-1)
+        return SparseTargets(idx.to(torch.int32), screen[idx].to(torch.float64))
+
+    def to(self, device, non_blocking=False):
+        return SparseTargets(self.idx.to(device, non_blocking=non_blocking), self.xyz.to(device, non_blocking=non_blocking))
+
+    def pin_memory(self):
+        return SparseTargets(self.idx.pin_memory(), self.xyz.pin_memory())
+
+    def __len__(self):
+        return self.idx.shape[0]
+
+
+def origin_rows(origin, n_rays):
+    """-> (rows float64 [r,3] contiguous, rays_per_origin).  Accepts the reference's [N,3] layout, an expanded
+    (stride-0) tensor as captured_data.generate_ray returns it (captured_data.py:38), or r rows with r | N."""
+    if origin.dim() == 1:
+        origin = origin.reshape(1, 3)
+    if origin.dim() != 2 or origin.shape[1] != 3:
+        raise ValueError(f"origin must be [N,3], [r,3] or [3], got {tuple(origin.shape)}")
+    r = origin.shape[0]
+    if r == n_rays and n_rays > 1 and origin.stride(0) == 0:
+        return origin[:1].contiguous(), max(n_rays, 1)
+    if r == n_rays or n_rays == 0:
+        return origin.contiguous(), 1
+    if r < 1 or n_rays % r:
+        raise ValueError(f"{r} origin rows do not divide {n_rays} rays")
+    return origin.contiguous(), n_rays // r
+
+
+class RayLossStep(torch.autograd.Function):
+    """loss and d loss/d vertices from ONE drt_ray_loss_step call (six launches, no dense per-ray output)."""
+
+    @staticmethod
+    def forward(ctx, vertices, origin, rpo, ray_dir, screen, valid, targets, mesh, int_ior, ext_ior, n_paths, ev_after_fwd):
+        dev = mesh.device
+        V = vertices.detach().contiguous()
+        o, d = origin.detach(), ray_dir.detach().contiguous()
+        if not (V.dtype == o.dtype == d.dtype == torch.float64):
+            raise TypeError("ray_loss works in float64 like the reference (captured_data.py:9)")
+        if d.dim() != 2 or d.shape[1] != 3:
+            raise ValueError("ray_dir must be [N,3]")
+        if V.shape[0] != mesh.n_verts:
+            raise ValueError(f"vertices has {V.shape[0]} rows, the mesh was built with {mesh.n_verts}")
+        n = d.shape[0]
+        scr = val = idx = xyz = None
+        n_tgt = 0
+        if targets is not None:
+            mode, idx, xyz, n_tgt = 1, targets.idx, targets.xyz, len(targets)
+        else:
+            mode = 0
+            scr = screen.detach().contiguous()
+            if scr.dtype != torch.float64 or scr.shape != d.shape:
+                raise ValueError("screen must be float64 [N,3]")
+            if valid is not None:
+                if valid.shape != (n,):
+                    raise ValueError("valid must be [N]")
+                val = valid.to(torch.bool).contiguous()
+        need_grad = ctx.needs_input_grad[0]
+        loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        grad_V = torch.zeros_like(V) if need_grad else None
+        _lib.call("drt_ray_loss_step", mesh._h, _ptr(V), _ptr(o), int(rpo), _ptr(d), n, float(ext_ior), float(int_ior), mode,
+                  _ptr(scr), _ptr(val), _ptr(idx), _ptr(xyz), n_tgt, _ptr(loss), _ptr(grad_V), _ptr(n_paths),
+                  C.c_void_p(ev_after_fwd or 0), optix._stream_ptr(dev))
+        st = torch.cuda.current_stream(dev)
+        for t in (V, o, d, scr, val, idx, xyz):  # consumed asynchronously on the stream
+            if t is not None:
+                t.record_stream(st)
+        ctx.save_for_backward(grad_V)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (grad_V,) = ctx.saved_tensors
+        return (grad_V * g_loss if grad_V is not None else None,) + (None,) * 11
+
+
+def ray_loss(scene, origin, ray_dir, screen=None, valid=None, targets=None, n_paths=None, ev_after_fwd=None):
+    """sum over valid & traced rays of || out_dir - normalize(screen - out_ori) ||^2  (optim.py:96-106).
+
+    Either the reference's dense pair (`screen` [N,3], `valid` [N] or None) or `targets` = SparseTargets.
+    `origin`: [N,3], expanded/[1,3] (one origin for all rays) or [r,3] with r | N (ray i starts at row i // (N/r)).
+    `n_paths`: optional int32[1] device tensor receiving the number of valid two-bounce paths."""
+    if (screen is None) == (targets is None):
+        raise ValueError("give either screen (+valid) or targets")
+    rows, rpo = origin_rows(origin, ray_dir.shape[0])
+    return RayLossStep.apply(scene.vertices, rows, rpo, ray_dir, screen, valid, targets, scene.optix_mesh, _R.intIOR, _R.extIOR,
+                             n_paths, ev_after_fwd)
+
+
+def ray_loss_view(scene, view):
+    """`view` = captured_data.CompactView (one origin row, ray_dir, sparse targets) on the scene's device."""
+    return ray_loss(scene, view.origin, view.ray_dir, targets=view.targets)

@@ -8,9 +8,10 @@ import torch
 
 from . import views as _views
 from . import DiffRender as R
+from .captured_data import CompactViews
 
 
-class SyntheticData:
+class SyntheticData(CompactViews):
     def __init__(self, target_vertices, faces, resy, resx, n_views=72, num_view=72, cuda_device=0, screen_dist=100.0,
                  int_ior=None, seed=0):
         self.resy, self.resx, self.num_view, self.n_views = resy, resx, num_view, n_views

@@ -59,6 +59,27 @@ def generate_ray(resy, resx, K_inverse, R_inverse, device="cpu", dtype=torch.flo
     return origin.contiguous(), d.contiguous()
 
 
+def generate_ray_device(resy, resx, K_inverse, R_inverse, device, out_dir=None):
+    """captured_data.generate_ray (captured_data.py:23-40) as ONE kernel (drt_generate_rays): -> (origin [1,3],
+    ray_dir [resy*resx,3]) on `device`; `origin.expand_as(ray_dir)` is what the reference returns.  Agrees with
+    `generate_ray` to a few ulp (the reference's two matmuls leave the summation order to the BLAS)."""
+    import ctypes as C
+
+    from . import _lib
+    dev = torch.device(device)
+    Ki = torch.as_tensor(np.asarray(K_inverse), dtype=torch.float64).to(dev).contiguous()
+    Ri = torch.as_tensor(np.asarray(R_inverse), dtype=torch.float64).to(dev).contiguous()
+    if Ki.shape != (3, 3) or Ri.shape != (4, 4):
+        raise ValueError("K_inverse must be [3,3] and R_inverse [4,4]")
+    origin = torch.empty((1, 3), dtype=torch.float64, device=dev)
+    d = out_dir if out_dir is not None else torch.empty((resy * resx, 3), dtype=torch.float64, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    with torch.cuda.device(dev):
+        _lib.call("drt_generate_rays", int(resy), int(resx), p(Ki), p(Ri), p(origin), p(d),
+                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    return origin, d
+
+
 def view_batch(cams, resy, resx, device="cpu", out_origin=None, out_dir=None):
     """Rays of several views concatenated view-major: [len(cams)*resy*resx, 3] each."""
     n = resy * resx

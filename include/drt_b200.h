@@ -134,6 +134,47 @@ DRT_API int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, 
                           const int32_t* rec, const int32_t* rec_count, int64_t N, double* g_out_dir, double* loss_sum,
                           void* stream);
 
+/*
+ * The whole ray iteration on one batch of rays in one call, with NO dense per-ray output
+ * (replaces Loss_calculator.ray_loss + loss.backward(), optim.py:91-108,210, i.e.
+ * Scene.render_transparent DiffRender.py:420-432 -> target = normalize(screen - out_ori.detach())
+ * -> sum over valid&mask of |out_dir - target|^2 -> d loss / d vertices):
+ * six launches -- Q1, refract, Q2, refract, Q3 (hit ids and exit rays bit-identical to
+ * drt_trace_fwd) and one kernel over the valid paths that adds the loss terms and scatter-adds
+ * the analytic vertex gradient.  Rays that miss write nothing; d loss/d out_dir is never stored.
+ *   origin          float64[ceil(N/rays_per_origin),3]: ray i starts at row i / rays_per_origin.
+ *                   rays_per_origin = 1 is the reference layout (one row per ray); a pinhole view
+ *                   has ONE origin (captured_data.py:38 expands it), so pass its row once with
+ *                   rays_per_origin = rays per view (several views per call: one row per view).
+ *   dir             float64[N,3]
+ *   target_mode 0   dense targets as the reference holds them: screen float64[N,3] and valid
+ *                   uint8[N] (NULL = all true) -- captured_data.py:101-104
+ *   target_mode 1   sparse targets: tgt_idx int32[n_tgt] = ray indices with a measured screen
+ *                   point, strictly ascending, tgt_xyz float64[n_tgt,3]; every other ray is
+ *                   `valid = False` (captured_data.py:104: valid = screen_pixel[:,0] != 0)
+ *   loss_sum        float64[1], ACCUMULATED into (caller zeroes)
+ *   grad_V          float64[nV,3], ACCUMULATED into; NULL = loss value only
+ *   n_paths         optional int32[1]: number of valid two-bounce paths of this batch (before the
+ *                   `valid` filter) = mask.sum() of render_transparent
+ *   ev_after_fwd    optional cudaEvent_t recorded on `stream` between the forward wavefront and the
+ *                   loss/backward kernel (phase timing for bench.py); NULL = none
+ * Scratch (72 B per ray of capacity) lives in the handle and is reused by later calls.
+ */
+DRT_API int drt_ray_loss_step(const drt_bvh* bvh, const double* V64, const double* origin, int64_t rays_per_origin,
+                      const double* dir, int64_t N, double ext_ior, double int_ior, int target_mode, const double* screen,
+                      const uint8_t* valid, const int32_t* tgt_idx, const double* tgt_xyz, int64_t n_tgt, double* loss_sum,
+                      double* grad_V, int32_t* n_paths, void* ev_after_fwd, void* stream);
+
+/*
+ * Replaces captured_data.generate_ray -- captured_data.py:23-40 (the pinhole sets build their rays
+ * with it, captured_data.py:149): pixel (x, y, 1), x fastest, through K_inverse float64[3,3] and
+ * R_inverse float64[4,4] (camera-to-world, row-major) -> dir float64[resy*resx,3] normalised and
+ * origin3 float64[3] = the camera centre (the reference returns it expanded to [N,3]; pass it to
+ * drt_ray_loss_step with rays_per_origin = resy*resx).  All pointers are device pointers.
+ */
+DRT_API int drt_generate_rays(int32_t resy, int32_t resx, const double* K_inverse, const double* R_inverse, double* origin3,
+                      double* dir, void* stream);
+
 /* Text of the last error on this thread ("" if none).  Never NULL. */
 DRT_API const char* drt_last_error(void);
 

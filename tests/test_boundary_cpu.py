@@ -123,3 +123,30 @@ def test_captured_data_loader_schema_and_soft_mask(tmp_path):
     o_ref, d_ref = views.generate_ray(12, 16, cams[1][3], cams[1][2])
     assert torch.allclose(ray_dir, d_ref) and torch.allclose(origin, o_ref) and mask.shape == (12, 16)
     assert torch.allclose(cam[0] @ cam[2], torch.eye(4, dtype=torch.float64), atol=1e-12)
+
+
+def test_compact_view_and_origin_layout_host_logic():
+    """CompactView / SparseTargets / origin_rows (the lossless compact host format of the fused ray-loss step)."""
+    import torch
+    from drt_b200 import losses, views
+    from drt_b200.captured_data import CompactView
+    cam = views.turntable_cameras(np.array([[-1.0, -1, -1], [1, 1, 1]]), 6, 8, 72)[5]
+    o, d = views.generate_ray(6, 8, cam[3], cam[2])
+    screen = torch.zeros_like(d)
+    screen[[3, 17, 40]] = torch.tensor([[1.0, 2, 3], [4, 5, 6], [7, 8, 9]], dtype=torch.float64)
+    valid = screen[:, 0] != 0
+    cv = CompactView.from_reference_view((screen, valid, None, o, d, None))
+    assert cv.origin.shape == (1, 3) and torch.equal(cv.origin[0], o[0])
+    assert cv.targets.idx.tolist() == [3, 17, 40] and cv.targets.idx.dtype == torch.int32
+    assert torch.equal(cv.targets.xyz, screen[[3, 17, 40]])
+    assert cv.h2d_bytes() == 24 + 48 * 24 + 3 * 28
+    o2 = o.clone()
+    o2[5, 0] += 1e-9                                      # calibrated per-pixel origins stay per ray
+    assert CompactView.from_reference_view((screen, valid, None, o2, d, None)).origin.shape == (48, 3)
+    assert losses.origin_rows(o, 48)[1] == 1
+    assert losses.origin_rows(o[:1].expand(48, 3), 48)[1] == 48
+    assert losses.origin_rows(o[:4], 48)[1] == 12 and losses.origin_rows(o[0], 48)[1] == 48
+    with pytest.raises(ValueError):
+        losses.origin_rows(o[:5], 48)
+    with pytest.raises(TypeError):
+        losses.SparseTargets(torch.zeros(3, dtype=torch.int64), torch.zeros((3, 3), dtype=torch.float64))

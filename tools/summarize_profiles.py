@@ -92,5 +92,9 @@ if os.path.exists(rep):
     fwd = [v for k, v in summ.items() if k.startswith("wf_")]
     if fwd:
         allj["trace_fwd"] = {"dram_bytes_per_ray": sum(v["dram_bytes_per_launch"] for v in fwd) / 5529600, "from": tag}
+    # the same five stages inside drt_ray_loss_step (ls_q1/r1/q2/r2/q3; ls_loss_bwd is the backward)
+    ls = [v for k, v in summ.items() if k.startswith("ls_") and not k.startswith("ls_loss_bwd")]
+    if ls:
+        allj["loss_step_fwd"] = {"dram_bytes_per_ray": sum(v["dram_bytes_per_launch"] for v in ls) / 5529600, "from": tag}
     json.dump(allj, open(js, "w"), indent=1)
     print("wrote ncu full summary:", list(summ))
