@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--ref-views", type=int, default=8, help="views per step of the CPU reference arm")
     ap.add_argument("--cpu-views", type=int, default=36, help="views of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=4, help="views per H2D chunk / library call of the compact e2e path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-chain-gpu", action="store_true", help="skip the supplementary R-GPU baseline")
     ap.add_argument("--refit", action="store_true", help="refit instead of rebuilding the BVH each step")
@@ -363,44 +364,51 @@ def run_b200(args):
                           stream_ptr())
                 out_dir.backward(gds[b])
                 return None
-            return upload, compute, int(n_total * (24 + 24 + 24 + 1))
+            return upload, compute, int(n_total * (24 + 24 + 24 + 1)), len(cams)
 
         def make_compact_layout():
             """the loader's lossless compact form (captured_data.CompactView): one origin row per pinhole view, ray_dir,
             sorted indices + screen points of the measured pixels only"""
-            cvs = [CompactView.from_reference_view((view_slice(host[2], j), view_slice(host[3], j), None, view_slice(host[0], j),
-                                                    view_slice(host[1], j), None)).pin_memory() for j in range(len(cams))]
+            per_view = [CompactView.from_reference_view((view_slice(host[2], j), view_slice(host[3], j), None, view_slice(host[0], j),
+                                                         view_slice(host[1], j), None)) for j in range(len(cams))]
+            ch = max(1, args.e2e_chunk)
+            if any(c.origin.shape[0] != 1 for c in per_view):
+                ch = 1
+            # the loader's batches: `ch` views per H2D chunk and per drt_ray_loss_step call (CompactView.concat)
+            cvs = [(CompactView.concat(per_view[a:a + ch]) if ch > 1 else per_view[a]).pin_memory() for a in range(0, len(per_view), ch)]
+            del per_view
             max_t = max([len(c.targets) for c in cvs] + [1])
             rows = max([c.origin.shape[0] for c in cvs] + [1])
-            bufs = [dict(o=torch.empty((rows, 3), dtype=torch.float64, device=dev), d=torch.empty((n_pix, 3), dtype=torch.float64, device=dev),
+            max_n = max([c.ray_dir.shape[0] for c in cvs] + [1])
+            bufs = [dict(o=torch.empty((rows, 3), dtype=torch.float64, device=dev), d=torch.empty((max_n, 3), dtype=torch.float64, device=dev),
                          idx=torch.empty(max_t, dtype=torch.int32, device=dev), xyz=torch.empty((max_t, 3), dtype=torch.float64, device=dev))
                     for _ in range(nbuf)]
 
             def upload(j, b):
                 c, B = cvs[j], bufs[b]
-                nt, r = len(c.targets), c.origin.shape[0]
+                nt, r, n = len(c.targets), c.origin.shape[0], c.ray_dir.shape[0]
                 B["o"][:r].copy_(c.origin, non_blocking=True)
-                B["d"].copy_(c.ray_dir, non_blocking=True)
+                B["d"][:n].copy_(c.ray_dir, non_blocking=True)
                 B["idx"][:nt].copy_(c.targets.idx, non_blocking=True)
                 B["xyz"][:nt].copy_(c.targets.xyz, non_blocking=True)
 
             def compute(j, b):
                 c, B = cvs[j], bufs[b]
-                nt, r = len(c.targets), c.origin.shape[0]
-                return losses.ray_loss_view(scene, CompactView(B["o"][:r], B["d"], losses.SparseTargets(B["idx"][:nt], B["xyz"][:nt])))
+                nt, r, n = len(c.targets), c.origin.shape[0], c.ray_dir.shape[0]
+                return losses.ray_loss_view(scene, CompactView(B["o"][:r], B["d"][:n], losses.SparseTargets(B["idx"][:nt], B["xyz"][:nt])))
             h2d = sum(c.h2d_bytes() for c in cvs)
             if world > 1:
                 t = torch.tensor([h2d], dtype=torch.float64, device=dev)
                 dist.all_reduce(t)
                 h2d = t.item()
-            return upload, compute, int(h2d)
+            return upload, compute, int(h2d), len(cvs)
 
-        def time_e2e(upload, compute):
+        def time_e2e(upload, compute, n_chunks):
             def e2e_step():
                 V.grad = None
                 loss_buf.zero_()
                 scene.update_verticex(V)
-                for j in range(len(cams)):
+                for j in range(n_chunks):
                     b = j % nbuf
                     with torch.cuda.stream(copy_stream):
                         copy_stream.wait_event(free[b])            # the compute that last used this buffer is done
@@ -437,8 +445,8 @@ def run_b200(args):
             return te.item() / k_e2e, k_e2e
 
         d2h = int(world * (nV * 24 + 8))
-        up, comp, h2d = make_reference_layout()
-        ms, k_e2e = time_e2e(up, comp)
+        up, comp, h2d, nch = make_reference_layout()
+        ms, k_e2e = time_e2e(up, comp, nch)
         e2e_ref_layout = {"value": n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": k_e2e, "h2d_bytes_per_step": h2d,
                           "d2h_bytes_per_step": d2h,
                           "note": "per-view H2D of the reference's dense view tensors (origin/ray_dir/screen_pixel f64 [N,3] + valid, "
@@ -446,13 +454,13 @@ def run_b200(args):
         del up, comp
         torch.cuda.empty_cache()
         if args.loss_path == "step":
-            up, comp, h2d = make_compact_layout()
-            ms, k_e2e = time_e2e(up, comp)
+            up, comp, h2d, nch = make_compact_layout()
+            ms, k_e2e = time_e2e(up, comp, nch)
             e2e = {"value": n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": k_e2e, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h,
                    "note": "per-view H2D from pinned host memory of the loader's lossless compact view (captured_data.CompactView: "
                            "one origin row per pinhole view, ray_dir f64 [N,3], int32 index + f64 screen point of the measured pixels "
-                           "only), double-buffered on a copy stream; losses.ray_loss_view per view; D2H of grad_V and loss"}
+                           "only), %d views per chunk, double-buffered on a copy stream; losses.ray_loss_view per chunk; D2H of grad_V and loss" % max(1, args.e2e_chunk)}
         else:
             e2e, e2e_ref_layout = e2e_ref_layout, None
     sampler.stop()

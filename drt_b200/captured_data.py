@@ -62,6 +62,19 @@ class CompactView:
         one = origin.shape[0] > 0 and bool((origin == origin[:1]).all())
         return CompactView(origin[:1].clone() if one else origin, ray_dir, SparseTargets.from_dense(screen, valid), mask, cam)
 
+    @staticmethod
+    def concat(views):
+        """Several single-origin views as ONE batch for one drt_ray_loss_step call: origin [n_views,3] (ray i starts
+        at row i // rays_per_view), ray_dir concatenated view-major, target indices offset into the batch.  All views
+        must have the same ray count and one origin row each."""
+        from .losses import SparseTargets
+        n = views[0].ray_dir.shape[0]
+        if any(v.origin.shape[0] != 1 or v.ray_dir.shape[0] != n for v in views):
+            raise ValueError("concat needs single-origin views of equal ray count")
+        idx = torch.cat([v.targets.idx + k * n for k, v in enumerate(views)])
+        return CompactView(torch.cat([v.origin for v in views]), torch.cat([v.ray_dir for v in views]),
+                           SparseTargets(idx, torch.cat([v.targets.xyz for v in views])))
+
     def pin_memory(self):
         pin = lambda t: t.pin_memory() if torch.cuda.is_available() else t  # noqa: E731
         return CompactView(pin(self.origin), pin(self.ray_dir), self.targets.pin_memory() if torch.cuda.is_available()
@@ -88,6 +101,14 @@ class CompactViews:
 
     def get_view_compact(self, V_index):
         return self.compact(V_index).to(self.device)
+
+    def compact_batch(self, V_indices):
+        """pinned host batch of several views (CompactView.concat), cached per index tuple"""
+        key = tuple(int(i) for i in V_indices)
+        cache = self.__dict__.setdefault("_compact_batches", {})
+        if key not in cache:
+            cache[key] = CompactView.concat([self.compact(i) for i in key]).pin_memory()
+        return cache[key]
 
 
 class Data(CompactViews):

@@ -56,6 +56,7 @@ struct Tuning {
     int bwd_merge = -1;  // DRT_BWD_MERGE = 0 | 1 forces the run-merged backward scatter off / on (default: by rays per vertex)
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
     int thresh = 32;
+    int pol[3];  // make_policy(thresh, vote) of the three query stages: DRT_FWD_THRESH / DRT_VOTE, per stage DRT_THRESH_Q1.. / DRT_VOTE_Q1..
     int minb = 8;
     Tuning()
     {
@@ -65,6 +66,19 @@ struct Tuning {
 
         const char* t = getenv("DRT_FWD_THRESH");
         if (t && atoi(t) >= 1 && atoi(t) <= 32) thresh = atoi(t);
+        const char* vt = getenv("DRT_VOTE");
+        const int vote = (vt && atoi(vt) >= 0 && atoi(vt) <= 31) ? atoi(vt) : 0;
+        for (int q = 0; q < 3; ++q) {
+            char name[32];
+            int th = thresh, vo = vote;
+            snprintf(name, sizeof name, "DRT_THRESH_Q%d", q + 1);
+            const char* a = getenv(name);
+            if (a && atoi(a) >= 1 && atoi(a) <= 32) th = atoi(a);
+            snprintf(name, sizeof name, "DRT_VOTE_Q%d", q + 1);
+            const char* c = getenv(name);
+            if (c && atoi(c) >= 0 && atoi(c) <= 31) vo = atoi(c);
+            pol[q] = make_policy(th, vo);
+        }
         const char* ol = getenv("DRT_ONE_LAUNCH");
         if (ol && !strcmp(ol, "1")) one_launch = true;
         const char* pl = getenv("DRT_PREFER_L1");
@@ -109,6 +123,7 @@ struct drt_bvh {
     double* park = nullptr;    size_t capPk = 0; // loss step: parked rays, 6 component columns of capPk/6 slots
     int* listM = nullptr;      size_t capLM = 0; // loss step: slots of L that survive both refractions
     int* listS = nullptr;      size_t capLS = 0; // loss step: slots of L whose exit ray is unoccluded (the valid paths)
+    int* tbucket = nullptr;    size_t capTb = 0; // loss step: bucket table of the sparse screen targets
     unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
     int work_slot = 0;
     int fused_blocks_per_sm = 0;                 // co-resident blocks of wf_fused_kernel<8> (0: no cooperative launch)
@@ -291,7 +306,7 @@ int drt_bvh_destroy(drt_bvh* b)
     if (!b) return DRT_OK;
     DeviceGuard g(b->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {b->listA, b->listB, b->park, b->listM, b->listS, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
+    void* ptrs[] = {b->listA, b->listB, b->park, b->listM, b->listS, b->tbucket, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -392,7 +407,7 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
         CU(cudaMemsetAsync(ctl, 0, 4 * sizeof(unsigned long long), st));
         int* countL = (int*)(ctl + 3);
         int* countM = countL + 1;
-        const int thresh = tuning().thresh;
+        const int* pol = tuning().pol;
         // bulk zero-fill needs 16-byte aligned output rows for every multiple-of-32 ray index
         const bool bulk_ok = tuning().bulk && !(((uintptr_t)out_ori | (uintptr_t)out_dir | (uintptr_t)mask3 | (uintptr_t)hit1) & 15u);
         const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
@@ -402,7 +417,7 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
         if (tuning().one_launch && b->fused_blocks_per_sm > 0) {
             // the whole wavefront as ONE cooperative launch (grid-wide barriers between the stages)
             FwdArgs fa{b->view(), V64, origin, dir, (int)N, ext_ior, int_ior, out_ori, out_dir, mask3, hit1, b->listA, b->listB,
-                       (int4*)rec, rec_count, ctl, thresh, bulk_ok ? 1 : 0};
+                       (int4*)rec, rec_count, ctl, {pol[0], pol[1], pol[2]}, bulk_ok ? 1 : 0};
             void* kargs[] = {&fa};
             const bool six = minb == 6 && b->fused6_blocks_per_sm > 0;
             const int per_sm = six ? b->fused6_blocks_per_sm : b->fused_blocks_per_sm;
@@ -421,13 +436,13 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
         else if (minb == 6) KERNEL<6><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
         else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
     } while (0)
-        DRT_LAUNCH_Q(wf_q1_kernel, b->view(), j1, (int)N, ctl + 0, thresh);
+        DRT_LAUNCH_Q(wf_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
         wf_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, origin, dir, ext_ior, int_ior, out_ori, out_dir, mask3, b->listA, countL);
         ExitJob j2{out_ori, out_dir, b->listA};
-        DRT_LAUNCH_Q(wf_q2_kernel, b->view(), j2, countL, ctl + 1, thresh);
+        DRT_LAUNCH_Q(wf_q2_kernel, b->view(), j2, countL, ctl + 1, pol[1]);
         wf_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, out_ori, out_dir, mask3, b->listA, countL, b->listB, countM);
         OcclusionJob j3{out_ori, out_dir, mask3, b->listB, (int4*)rec, rec_count};
-        DRT_LAUNCH_Q(wf_q3_kernel, b->view(), j3, countM, ctl + 2, thresh);
+        DRT_LAUNCH_Q(wf_q3_kernel, b->view(), j3, countM, ctl + 2, pol[2]);
 #undef DRT_LAUNCH_Q
         g_launches += 4;
     }
@@ -524,13 +539,19 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
     int* countL = (int*)(ctl + 3);
     int* countM = countL + 1;
     int* countS = (int*)(ctl + 4);
-    const int thresh = tuning().thresh;
+    const int* pol = tuning().pol;
     const int minb = tuning().minb;
     const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
     const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
     const RaySrc rays{origin, dir, (int)rays_per_origin};
     const Park park{b->park, (int64_t)(b->capPk / 6)};
-    const TargetSrc tgt{screen, valid, tgt_idx, tgt_xyz, (int)n_tgt, target_mode};
+    const int n_buckets = (int)(N >> kTgtShift) + 2;
+    if (target_mode == 1) {
+        if ((rc = ensure(b->tbucket, b->capTb, (size_t)n_buckets))) return rc;
+        tgt_bucket_kernel<<<blocks_for(n_buckets, 256), 256, 0, st>>>(tgt_idx, (int)n_tgt, n_buckets, b->tbucket);
+        ++g_launches;
+    }
+    const TargetSrc tgt{screen, valid, tgt_idx, tgt_xyz, b->tbucket, (int)n_tgt, target_mode};
 #define DRT_LAUNCH_Q(KERNEL, ...)                                                           \
     do {                                                                                    \
         if (minb == 10) KERNEL<10><<<pg, 128, 0, st>>>(__VA_ARGS__);                        \
@@ -540,13 +561,13 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
         else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
     } while (0)
     LossEntryJob j1{rays, b->listA, countL};
-    DRT_LAUNCH_Q(ls_q1_kernel, b->view(), j1, (int)N, ctl + 0, thresh);
+    DRT_LAUNCH_Q(ls_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
     ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park);
     LossExitJob j2{park, b->listA};
-    DRT_LAUNCH_Q(ls_q2_kernel, b->view(), j2, countL, ctl + 1, thresh);
+    DRT_LAUNCH_Q(ls_q2_kernel, b->view(), j2, countL, ctl + 1, pol[1]);
     ls_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, b->listA, countL, park, b->listM, countM);
     LossOcclusionJob j3{park, b->listM, b->listS, countS};
-    DRT_LAUNCH_Q(ls_q3_kernel, b->view(), j3, countM, ctl + 2, thresh);
+    DRT_LAUNCH_Q(ls_q3_kernel, b->view(), j3, countM, ctl + 2, pol[2]);
 #undef DRT_LAUNCH_Q
     if (ev_after_fwd) CU(cudaEventRecord((cudaEvent_t)ev_after_fwd, st));
     const bool merge = tuning().bwd_merge == 1 || (tuning().bwd_merge < 0 && N / std::max(b->nV, 1) > 5000);

@@ -131,6 +131,31 @@ __device__ __forceinline__ void walk(const BvhView& B, const RayQ& q, float tmax
     }
 }
 
+// Same walk with a WARP VOTE on when to stop: lanes step together, one node step (or one leaf push) per
+// iteration, and the warp leaves the loop as soon as `vote` lanes are blocked -- leaf queue full, or walk
+// finished with leaves still queued -- instead of waiting until every lane is (walk() above is the
+// vote = 32 case).  The blocked lanes then get their triangle tests while the others still have a short
+// queue; with the per-lane loop a lane that has filled its queue idles until the SLOWEST lane of the warp
+// has filled its own.  All 32 lanes must call this.
+__device__ __forceinline__ void walk_vote(const BvhView& B, const RayQ& q, float tmax, int& node, int* stack, int& sp, int& nd,
+                                          int vote)
+{
+    const unsigned FULL = 0xffffffffu;
+    for (;;) {
+        if (node != kDone && nd < kDefer) {
+            if (node >= 0) {
+                node = node_step(B, q, tmax, node, stack, sp);
+            } else {
+                stack[kStackDepth - 1 - nd] = node;
+                ++nd;
+                node = sp ? stack[--sp] : kDone;
+            }
+        }
+        const bool cont = node != kDone && nd < kDefer;
+        if (!__any_sync(FULL, cont) || __popc(__ballot_sync(FULL, nd > 0 && !cont)) >= vote) break;
+    }
+}
+
 // test the queued leaves; returns true as soon as ANY is satisfied
 template <bool ANY>
 __device__ __forceinline__ bool drain(const BvhView& B, const QRay& r, int* stack, int& nd, double& t_best, int& id_best,

@@ -45,9 +45,14 @@ __device__ __forceinline__ int warp_append(int* __restrict__ counter, bool pred)
 //                                void retire(int item, int id, double t).
 // Lanes step their traversals together; once `thresh` of the live lanes have finished, those retire
 // and are refilled from the global work counter (thresh = 32: refill only when the whole warp is done).
+// `policy` = thresh | vote << 8; vote = 0: every lane walks until its own leaf queue is full (walk),
+// vote = 1..31: the warp drains as soon as that many lanes are blocked (walk_vote).
+__host__ __device__ constexpr int make_policy(int thresh, int vote) { return thresh | (vote << 8); }
+
 template <bool ANY, class Job>
-__device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int total, unsigned long long* work, int thresh)
+__device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int total, unsigned long long* work, int policy)
 {
+    const int thresh = policy & 0xff, vote = policy >> 8;
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -92,7 +97,8 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
         const int need = min(thresh, __popc(live));
 
         for (;;) {
-            walk(B, q, tmax, node, stack, sp, nd);
+            if (vote) walk_vote(B, q, tmax, node, stack, sp, nd, vote);
+            else walk(B, q, tmax, node, stack, sp, nd);
             if (drain<ANY>(B, q.r, stack, nd, t_best, id_best, tmax)) { node = kDone; sp = 0; }
             unsigned fin = __ballot_sync(FULL, item >= 0 && node == kDone);
             if (__popc(fin) >= need) break;
@@ -173,7 +179,7 @@ struct EntryJob {
 };
 
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) wf_q1_kernel(BvhView B, EntryJob job, int N, unsigned long long* work, int thresh)
+__global__ void __launch_bounds__(128, MINB) wf_q1_kernel(BvhView B, EntryJob job, int N, unsigned long long* work, int policy)
 {
     __shared__ ZeroTile zt;
     for (int j = threadIdx.x; j < 768 / 4; j += blockDim.x) reinterpret_cast<unsigned*>(zt.z)[j] = 0u;
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(128, MINB) wf_q1_kernel(BvhView B, EntryJob jo
     __syncthreads();
     if (job.zeros) job.zeros = &zt;
     job.issued = false;
-    persistent_query<false>(B, job, N, work, thresh);
+    persistent_query<false>(B, job, N, work, policy);
 }
 
 // ---- R1: refraction at the entry hit, dense over L ------------------------------------------------
@@ -239,9 +245,9 @@ struct ExitJob {
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) wf_q2_kernel(BvhView B, ExitJob job, const int* __restrict__ countL,
-                                                    unsigned long long* work, int thresh)
+                                                    unsigned long long* work, int policy)
 {
-    persistent_query<false>(B, job, *countL, work, thresh);
+    persistent_query<false>(B, job, *countL, work, policy);
 }
 
 // ---- R2: refraction at the exit hit, dense over L; survivors -> M ---------------------------------
@@ -317,9 +323,9 @@ struct OcclusionJob {
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) wf_q3_kernel(BvhView B, OcclusionJob job, const int* __restrict__ countM,
-                                                    unsigned long long* work, int thresh)
+                                                    unsigned long long* work, int policy)
 {
-    persistent_query<true>(B, job, *countM, work, thresh);
+    persistent_query<true>(B, job, *countM, work, policy);
 }
 
 // ---- all five stages in ONE cooperative launch ------------------------------------------------------
@@ -341,7 +347,7 @@ struct FwdArgs {
     int4* rec;
     int* rec_count;
     unsigned long long* ctl;  // [0..2] work counters of Q1,Q2,Q3; [3] = {countL, countM}
-    int thresh;
+    int policy[3];  // make_policy(thresh, vote) of Q1, Q2, Q3
     int bulk;
 };
 
@@ -358,21 +364,21 @@ __global__ void __launch_bounds__(128, MINB) wf_fused_kernel(FwdArgs a)
     int* countM = countL + 1;
     {
         EntryJob j{a.bulk ? &zt : nullptr, false, a.origin, a.dir, a.out_ori, a.out_dir, a.mask3, a.hit1, a.L, countL};
-        persistent_query<false>(a.B, j, a.N, a.ctl + 0, a.thresh);
+        persistent_query<false>(a.B, j, a.N, a.ctl + 0, a.policy[0]);
     }
     grid.sync();
     r1_body(a.B, a.V64, a.origin, a.dir, a.ext_ior, a.int_ior, a.out_ori, a.out_dir, a.mask3, a.L, countL);
     grid.sync();
     {
         ExitJob j{a.out_ori, a.out_dir, a.L};
-        persistent_query<false>(a.B, j, *(volatile int*)countL, a.ctl + 1, a.thresh);
+        persistent_query<false>(a.B, j, *(volatile int*)countL, a.ctl + 1, a.policy[1]);
     }
     grid.sync();
     r2_body(a.B, a.V64, a.ext_ior, a.int_ior, a.out_ori, a.out_dir, a.mask3, a.L, countL, a.M, countM);
     grid.sync();
     {
         OcclusionJob j{a.out_ori, a.out_dir, a.mask3, a.M, a.rec, a.rec_count};
-        persistent_query<true>(a.B, j, *(volatile int*)countM, a.ctl + 2, a.thresh);
+        persistent_query<true>(a.B, j, *(volatile int*)countM, a.ctl + 2, a.policy[2]);
     }
 }
 

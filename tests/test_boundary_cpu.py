@@ -140,6 +140,9 @@ def test_compact_view_and_origin_layout_host_logic():
     assert cv.targets.idx.tolist() == [3, 17, 40] and cv.targets.idx.dtype == torch.int32
     assert torch.equal(cv.targets.xyz, screen[[3, 17, 40]])
     assert cv.h2d_bytes() == 24 + 48 * 24 + 3 * 28
+    both = CompactView.concat([cv, cv])
+    assert both.origin.shape == (2, 3) and both.ray_dir.shape == (96, 3)
+    assert both.targets.idx.tolist() == [3, 17, 40, 51, 65, 88] and losses.origin_rows(both.origin, 96)[1] == 48
     o2 = o.clone()
     o2[5, 0] += 1e-9                                      # calibrated per-pixel origins stay per ray
     assert CompactView.from_reference_view((screen, valid, None, o2, d, None)).origin.shape == (48, 3)
