@@ -329,7 +329,7 @@ def run_b200(args):
     grad_norm = float(V.grad.norm().item())
 
     # ---- e2e: host buffers, copies inside the timed region ----------------------------------
-    e2e = e2e_ref_layout = None
+    e2e = e2e_ref_layout = e2e_pinhole = None
     if not args.no_e2e:
         from drt_b200.captured_data import CompactView
         host = [t.cpu().pin_memory() for t in (origin, ray_dir, screen, valid)]
@@ -403,7 +403,40 @@ def run_b200(args):
                 h2d = t.item()
             return upload, compute, int(h2d), len(cvs)
 
-        def time_e2e(upload, compute, n_chunks):
+        def make_pinhole_layout():
+            """Redmi-type sets (captured_data.py:149: rays derived from K and R with generate_ray): the host holds the
+            camera matrices and the measured screen points only; rays are generated on the device per view
+            (drt_generate_rays) right before the step consumes them."""
+            ch = max(1, args.e2e_chunk)
+            groups = [list(range(a, min(a + ch, len(cams)))) for a in range(0, len(cams), ch)]
+            tg = []
+            for g in groups:
+                tv = [losses.SparseTargets.from_dense(view_slice(host[2], j), view_slice(host[3], j)) for j in g]
+                tg.append(losses.SparseTargets(torch.cat([t.idx + k * n_pix for k, t in enumerate(tv)]), torch.cat([t.xyz for t in tv])).pin_memory())
+            Rinv = [torch.tensor(np.stack([cams[j][2] for j in g]), dtype=torch.float64).pin_memory() for g in groups]
+            Kinv = torch.tensor(np.asarray(cams[0][3]), dtype=torch.float64, device=dev) if cams else None
+            max_t = max([len(t) for t in tg] + [1])
+            bufs = [dict(o=torch.empty((ch, 3), dtype=torch.float64, device=dev), d=torch.empty((ch * n_pix, 3), dtype=torch.float64, device=dev),
+                         R=torch.empty((ch, 4, 4), dtype=torch.float64, device=dev),
+                         idx=torch.empty(max_t, dtype=torch.int32, device=dev), xyz=torch.empty((max_t, 3), dtype=torch.float64, device=dev))
+                    for _ in range(nbuf)]
+
+            def upload(j, b):
+                B, t = bufs[b], tg[j]
+                B["R"][:len(groups[j])].copy_(Rinv[j], non_blocking=True)
+                B["idx"][:len(t)].copy_(t.idx, non_blocking=True)
+                B["xyz"][:len(t)].copy_(t.xyz, non_blocking=True)
+
+            def compute(j, b):
+                B, t, g = bufs[b], tg[j], groups[j]
+                for k in range(len(g)):
+                    _lib.call("drt_generate_rays", resy, resx, p(Kinv), p(B["R"][k]), p(B["o"][k]), p(B["d"][k * n_pix:]), stream_ptr())
+                return losses.ray_loss_view(scene, CompactView(B["o"][:len(g)], B["d"][:len(g) * n_pix],
+                                                               losses.SparseTargets(B["idx"][:len(t)], B["xyz"][:len(t)])))
+            h2d = sum(len(g) * 128 + len(t) * 28 for g, t in zip(groups, tg))
+            return upload, compute, int(h2d), len(groups)
+
+        def time_e2e(upload, compute, n_chunks, tol=1e-6):
             def e2e_step():
                 V.grad = None
                 loss_buf.zero_()
@@ -441,7 +474,7 @@ def run_b200(args):
             te = torch.tensor([s2.elapsed_time(e2)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            assert abs(loss_host.item() - loss_val) <= 1e-6 * max(1.0, abs(loss_val)), (loss_host.item(), loss_val)
+            assert abs(loss_host.item() - loss_val) <= tol * max(1.0, abs(loss_val)), (loss_host.item(), loss_val)
             return te.item() / k_e2e, k_e2e
 
         d2h = int(world * (nV * 24 + 8))
@@ -461,6 +494,18 @@ def run_b200(args):
                    "note": "per-view H2D from pinned host memory of the loader's lossless compact view (captured_data.CompactView: "
                            "one origin row per pinhole view, ray_dir f64 [N,3], int32 index + f64 screen point of the measured pixels "
                            "only), %d views per chunk, double-buffered on a copy stream; losses.ray_loss_view per chunk; D2H of grad_V and loss" % max(1, args.e2e_chunk)}
+            del up, comp
+            torch.cuda.empty_cache()
+            if world == 1:
+                # supplementary: pinhole sets whose rays are DERIVED data (not the headline: its rays never cross PCIe).
+                # rays generated by the kernel agree with the host-generated ones to a few ulp, so a handful of the
+                # 49.8 M paths may take a different edge decision: the loss is checked to 1e-4 only
+                up, comp, h2d, nch = make_pinhole_layout()
+                ms, k_e2e = time_e2e(up, comp, nch, tol=1e-4)
+                e2e_pinhole = {"value": n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": k_e2e,
+                               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                               "note": "pinhole view sets (captured_data.py:149): H2D of the camera matrices and the measured screen points "
+                                       "only; ray directions generated on the device per view by drt_generate_rays inside the timed region"}
         else:
             e2e, e2e_ref_layout = e2e_ref_layout, None
     sampler.stop()
@@ -541,7 +586,7 @@ def run_b200(args):
                        "int_ior": configs.INT_IOR, "valid_frac_rank0": valid_frac},
             "phases_ms": {"bvh_build": t_build_ms, "fwd": t_fwd_ms, "loss_grad": phases[2], "bwd": t_bwd_ms, "allreduce": t_ar_ms},
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
-            "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "e2e": e2e, "e2e_reference_layout": e2e_ref_layout, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "e2e": e2e, "e2e_reference_layout": e2e_ref_layout, "e2e_pinhole": e2e_pinhole, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "loss": loss_val, "grad_norm": grad_norm,
         }
         print(json.dumps(out), flush=True)
