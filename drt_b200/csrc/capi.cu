@@ -58,10 +58,6 @@ struct Tuning {
     int thresh = 32;
     int pol[3];  // make_policy(thresh, vote) of the three query stages: DRT_FWD_THRESH / DRT_VOTE, per stage DRT_THRESH_Q1.. / DRT_VOTE_Q1..
     int minb = 8;
-    // fused ray-loss step (loss_step.cuh): DRT_STAGED = 0 | 1 (bulk-copy staged refill), DRT_LS_THRESH[_Q1.._Q3], DRT_LS_VOTE[_Q1.._Q3]
-    bool staged = true;
-    int ls_thresh[3] = {32, 32, 32};
-    int ls_vote[3] = {8, 8, 8};
     Tuning()
     {
         const char* k = getenv("DRT_FWD_KERNEL");
@@ -82,21 +78,6 @@ struct Tuning {
             const char* c = getenv(name);
             if (c && atoi(c) >= 0 && atoi(c) <= 31) vo = atoi(c);
             pol[q] = make_policy(th, vo);
-        }
-        const char* sg = getenv("DRT_STAGED");
-        if (sg && !strcmp(sg, "0")) staged = false;
-        for (int q = 0; q < 3; ++q) {
-            char name[32];
-            const char* a = getenv("DRT_LS_THRESH");
-            if (a && atoi(a) >= 1 && atoi(a) <= 32) ls_thresh[q] = atoi(a);
-            snprintf(name, sizeof name, "DRT_LS_THRESH_Q%d", q + 1);
-            a = getenv(name);
-            if (a && atoi(a) >= 1 && atoi(a) <= 32) ls_thresh[q] = atoi(a);
-            a = getenv("DRT_LS_VOTE");
-            if (a && atoi(a) >= 0 && atoi(a) <= 31) ls_vote[q] = atoi(a);
-            snprintf(name, sizeof name, "DRT_LS_VOTE_Q%d", q + 1);
-            a = getenv(name);
-            if (a && atoi(a) >= 0 && atoi(a) <= 31) ls_vote[q] = atoi(a);
         }
         const char* ol = getenv("DRT_ONE_LAUNCH");
         if (ol && !strcmp(ol, "1")) one_launch = true;
@@ -143,8 +124,6 @@ struct drt_bvh {
     int* listM = nullptr;      size_t capLM = 0; // loss step: slots of L that survive both refractions
     int* listS = nullptr;      size_t capLS = 0; // loss step: slots of L whose exit ray is unoccluded (the valid paths)
     int* tbucket = nullptr;    size_t capTb = 0; // loss step: bucket table of the sparse screen targets
-    float* qpark = nullptr;    size_t capQp = 0; // loss step: float32 query copies of the parked rays (Q2), 6 columns
-    float* qpark2 = nullptr;   size_t capQ2 = 0; // loss step: float32 exit rays of the survivors (Q3), 6 columns
     unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
     int work_slot = 0;
     int fused_blocks_per_sm = 0;                 // co-resident blocks of wf_fused_kernel<8> (0: no cooperative launch)
@@ -327,7 +306,7 @@ int drt_bvh_destroy(drt_bvh* b)
     if (!b) return DRT_OK;
     DeviceGuard g(b->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {b->listA, b->listB, b->park, b->listM, b->listS, b->tbucket, b->qpark, b->qpark2, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
+    void* ptrs[] = {b->listA, b->listB, b->park, b->listM, b->listS, b->tbucket, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -550,27 +529,22 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
     if (target_mode == 0 && !screen) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: dense targets need screen[N,3]");
     if (target_mode == 1 && n_tgt > 0 && (!tgt_idx || !tgt_xyz)) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: sparse targets need tgt_idx and tgt_xyz");
     int rc;
-    const size_t slots = ((size_t)N + 31) / 32 * 32 + 32;  // list capacity: whole 32-slot batches (bulk copies never run past it)
-    if ((rc = ensure(b->listA, b->capLA, slots))) return rc;
-    if ((rc = ensure(b->park, b->capPk, 6 * slots))) return rc;
-    if ((rc = ensure(b->qpark, b->capQp, 6 * slots))) return rc;
-    if ((rc = ensure(b->qpark2, b->capQ2, 6 * slots))) return rc;
-    if ((rc = ensure(b->listM, b->capLM, slots))) return rc;
-    if ((rc = ensure(b->listS, b->capLS, slots))) return rc;
+    if ((rc = ensure(b->listA, b->capLA, (size_t)N))) return rc;
+    if ((rc = ensure(b->park, b->capPk, 6 * (size_t)N))) return rc;
+    if ((rc = ensure(b->listM, b->capLM, (size_t)N))) return rc;
+    if ((rc = ensure(b->listS, b->capLS, (size_t)N))) return rc;
     // control block: work counters of Q1,Q2,Q3 + {countL, countM} + {countS, -}
     unsigned long long* ctl = b->work + (size_t)(b->work_slot++ % (kWorkSlots / 8)) * 8;
     CU(cudaMemsetAsync(ctl, 0, 8 * sizeof(unsigned long long), st));
     int* countL = (int*)(ctl + 3);
     int* countM = countL + 1;
     int* countS = (int*)(ctl + 4);
-    const Tuning& tn = tuning();
-    const int minb = tn.minb;
+    const int* pol = tuning().pol;
+    const int minb = tuning().minb;
     const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
     const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
     const RaySrc rays{origin, dir, (int)rays_per_origin};
     const Park park{b->park, (int64_t)(b->capPk / 6)};
-    const QPark qpark{b->qpark, (int64_t)(b->capQp / 6 / 32 * 32)};
-    const QPark qpark2{b->qpark2, (int64_t)(b->capQ2 / 6 / 32 * 32)};
     const int n_buckets = (int)(N >> kTgtShift) + 2;
     if (target_mode == 1) {
         if ((rc = ensure(b->tbucket, b->capTb, (size_t)n_buckets))) return rc;
@@ -578,42 +552,23 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
         ++g_launches;
     }
     const TargetSrc tgt{screen, valid, tgt_idx, tgt_xyz, b->tbucket, (int)n_tgt, target_mode};
-    // bulk copies need 16-byte aligned sources; anything else reads its rays straight from global memory
-    const bool per_ray_origin = rays_per_origin == 1;
-    const bool q1_stage = tn.staged && !(((uintptr_t)dir | (per_ray_origin ? (uintptr_t)origin : 0)) & 15u);
-    const int pol1 = make_policy3(tn.ls_thresh[0], tn.ls_vote[0], q1_stage ? 1 : 0);
-    const int pol2 = make_policy3(tn.ls_thresh[1], tn.ls_vote[1], tn.staged ? 1 : 0);
-    const int pol3 = make_policy3(tn.ls_thresh[2], tn.ls_vote[2], tn.staged ? 1 : 0);
 #define DRT_LAUNCH_Q(KERNEL, ...)                                                           \
     do {                                                                                    \
-        if (minb == 10) KERNEL(10)<<<pg, 128, 0, st>>>(__VA_ARGS__);                        \
-        else if (minb == 8) KERNEL(8)<<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
-        else if (minb == 7) KERNEL(7)<<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
-        else if (minb == 6) KERNEL(6)<<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
-        else KERNEL(4)<<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
+        if (minb == 10) KERNEL<10><<<pg, 128, 0, st>>>(__VA_ARGS__);                        \
+        else if (minb == 8) KERNEL<8><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
+        else if (minb == 7) KERNEL<7><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
+        else if (minb == 6) KERNEL<6><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
+        else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
     } while (0)
-#define DRT_Q1_SHARED(M) ls_q1_kernel<M, false>
-#define DRT_Q1_PER_RAY(M) ls_q1_kernel<M, true>
-#define DRT_Q2(M) ls_q2_kernel<M>
-#define DRT_Q3(M) ls_q3_kernel<M>
-    if (per_ray_origin) {
-        LossEntryJob<true> j1{rays, b->listA, countL};
-        DRT_LAUNCH_Q(DRT_Q1_PER_RAY, b->view(), j1, (int)N, ctl + 0, pol1);
-    } else {
-        LossEntryJob<false> j1{rays, b->listA, countL};
-        DRT_LAUNCH_Q(DRT_Q1_SHARED, b->view(), j1, (int)N, ctl + 0, pol1);
-    }
-    ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park, qpark);
-    LossExitJob j2{{qpark}, b->listA};
-    DRT_LAUNCH_Q(DRT_Q2, b->view(), j2, countL, ctl + 1, pol2);
-    ls_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, b->listA, countL, park, b->listM, countM, qpark2);
-    LossOcclusionJob j3{{qpark2}, b->listM, b->listS, countS};
-    DRT_LAUNCH_Q(DRT_Q3, b->view(), j3, countM, ctl + 2, pol3);
+    LossEntryJob j1{rays, b->listA, countL};
+    DRT_LAUNCH_Q(ls_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
+    ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park);
+    LossExitJob j2{park, b->listA};
+    DRT_LAUNCH_Q(ls_q2_kernel, b->view(), j2, countL, ctl + 1, pol[1]);
+    ls_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, b->listA, countL, park, b->listM, countM);
+    LossOcclusionJob j3{park, b->listM, b->listS, countS};
+    DRT_LAUNCH_Q(ls_q3_kernel, b->view(), j3, countM, ctl + 2, pol[2]);
 #undef DRT_LAUNCH_Q
-#undef DRT_Q1_SHARED
-#undef DRT_Q1_PER_RAY
-#undef DRT_Q2
-#undef DRT_Q3
     if (ev_after_fwd) CU(cudaEventRecord((cudaEvent_t)ev_after_fwd, st));
     const bool merge = tuning().bwd_merge == 1 || (tuning().bwd_merge < 0 && N / std::max(b->nV, 1) > 5000);
     if (!grad_V)

@@ -79,8 +79,7 @@ __global__ void __launch_bounds__(256) tgt_bucket_kernel(const int32_t* __restri
     bucket[b] = lo;
 }
 
-// parked rays, component-major: component c of slot k at park[c * cap + k] (cap is a multiple of 32, so every
-// 32-slot batch of every column starts 128-byte aligned)
+// parked rays, component-major: component c of slot k at park[c * cap + k]
 struct Park {
     double* __restrict__ p;
     int64_t cap;
@@ -96,209 +95,37 @@ struct Park {
     }
 };
 
-// the float32 QUERY copy of a parked ray (= cast_ray of the float64 one: DiffRender.py:387-388), six
-// component columns of 32-slot batches = six 128-byte runs per batch -- what the bulk-copy engine stages
-struct QPark {
-    float* __restrict__ p;
-    int64_t cap;
-    __device__ __forceinline__ void store(int k, const QRay& r) const
-    {
-        p[k] = r.ox; p[cap + k] = r.oy; p[2 * cap + k] = r.oz;
-        p[3 * cap + k] = r.dx; p[4 * cap + k] = r.dy; p[5 * cap + k] = r.dz;
-    }
-    __device__ __forceinline__ void store_dead(int k) const { p[k] = __int_as_float(0x7fc00000); }  // NaN origin = nothing to trace
-    __device__ __forceinline__ QRay load(int k) const
-    {
-        return QRay{p[k], p[cap + k], p[2 * cap + k], p[3 * cap + k], p[4 * cap + k], p[5 * cap + k]};
-    }
-};
-
-// ---------------------------------------------------------------------------------------------------
-// Staged persistent query: the rays of a warp's NEXT 32-ray batch are copied global -> shared by the
-// bulk-copy engine (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) while the warp still traverses the
-// current one, so refilling a finished lane is a shared-memory read instead of a DRAM/L2 round trip that
-// stalls all 32 lanes.  That is what makes refilling before the whole warp is done (thresh < 32) pay: with
-// refills straight from global memory every threshold below 32 measured 15-20 % SLOWER on B200, the warp
-// scheduling model (tools/warp_sim) says 12-27 % fewer warp-wide steps if the refill is cheap.
-// Two buffers per warp: batch n in use, batch n+1 in flight / landed.
-// Job: kStageBytes, stage_issue(base, buf, mbar) [one lane], fetch(buf or nullptr, j, item, QRay&) -> bool,
-//      retire(item, id).
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
-{
-    unsigned ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok)
-                     : "r"(smem_u32(bar)), "r"(parity)
-                     : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-template <int BYTES>
-struct WarpStage {
-    alignas(128) unsigned char buf[2][BYTES];
-    alignas(8) unsigned long long mbar[2];
-};
-
-// policy bits: thresh | vote << 8 | staged << 16
-__host__ __device__ constexpr int make_policy3(int thresh, int vote, int staged) { return thresh | (vote << 8) | (staged << 16); }
-
-template <bool ANY, class Job>
-__device__ __forceinline__ void staged_query(const BvhView& B, Job& job, int total, unsigned long long* work, int policy,
-                                             WarpStage<Job::kStageBytes>* stg)
-{
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const int thresh = policy & 0xff, vote = (policy >> 8) & 0xff;
-    const bool staging = (policy >> 16) & 1;
-    int pbase0 = 0, pbase1 = 0;   // first ray of the batch assigned to buffer 0 / 1
-    unsigned phases = 0;          // bit b = parity the next completion of buffer b will have
-    int cur = 0;
-    bool started = false, more = total > 0;
-    int batch_base = 0, batch_next = 0, batch_end = 0;
-    bool batch_staged = false;
-
-    // claim a batch for buffer b and start its copy (full batches only; the last, partial one is read directly)
-    auto claim = [&](int b) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(work, 32ull);
-        base = __shfl_sync(FULL, base, 0);
-        const int bs = base >= (unsigned long long)total ? total : (int)base;
-        if (b) pbase1 = bs; else pbase0 = bs;
-        if (staging && lane == 0 && total - bs >= 32) job.stage_issue(bs, stg->buf[b], &stg->mbar[b]);
-    };
-    if (staging) {
-        if (lane == 0) {
-            mbar_init(&stg->mbar[0], 1);
-            mbar_init(&stg->mbar[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-    }
-    if (more) { claim(0); claim(1); }
-
-    int item = -1;
-    RayQ q;
-    float tmax = 0.f;
-    double t_best = 0.0;
-    int id_best = -1, node = kDone, sp = 0, nd = 0;
-    int stack[kStackDepth];
-
-    for (;;) {
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {  // a batch may run out mid-way: second pass opens the next one
-            unsigned idle = __ballot_sync(FULL, item < 0);
-            if (!idle || !more) break;
-            if (batch_next >= batch_end) {
-                if (started) { claim(cur); cur ^= 1; }  // every ray of the finished batch sits in a lane: its buffer is free
-                started = true;
-                const int base = cur ? pbase1 : pbase0;
-                if (base >= total) { more = false; break; }
-                const int cnt = min(32, total - base);
-                batch_staged = staging && cnt == 32;
-                if (batch_staged) {
-                    mbar_wait(&stg->mbar[cur], (phases >> cur) & 1u);
-                    phases ^= 1u << cur;
-                }
-                batch_base = batch_next = base;
-                batch_end = base + cnt;
-            }
-            if (item < 0) {
-                int cand = batch_next + __popc(idle & lt_mask);
-                if (cand < batch_end) {
-                    item = cand;
-                    t_best = INFINITY; id_best = -1; sp = 0; nd = 0; tmax = INFINITY; node = kDone;
-                    QRay r;
-                    if (job.fetch(batch_staged ? stg->buf[cur] : nullptr, cand - batch_base, cand, r) && B.nTris > 0) {
-                        q = ray_setup(B, r);
-                        node = 0;
-                    }
-                }
-            }
-            batch_next = min(batch_next + __popc(idle), batch_end);
-        }
-        const unsigned live = __ballot_sync(FULL, item >= 0);
-        if (!live) break;
-        const int need = min(thresh, __popc(live));
-        for (;;) {
-            if (vote) walk_vote(B, q, tmax, node, stack, sp, nd, vote);
-            else walk(B, q, tmax, node, stack, sp, nd);
-            if (drain<ANY>(B, q.r, stack, nd, t_best, id_best, tmax)) { node = kDone; sp = 0; }
-            unsigned fin = __ballot_sync(FULL, item >= 0 && node == kDone);
-            if (__popc(fin) >= need) break;
-        }
-        if (item >= 0 && node == kDone) {
-            job.retire(item, id_best);
-            item = -1;
-        }
-    }
-}
-
 // ---- Q1: entry query over all rays; only hits leave a trace ---------------------------------------
-// PER_RAY_ORIGIN = false: the origin row is shared by rpo consecutive rays (read straight from L1);
-// true: one origin row per ray, staged next to the direction.
-template <bool PER_RAY_ORIGIN>
 struct LossEntryJob {
-    static constexpr int kStageBytes = PER_RAY_ORIGIN ? 1536 : 768;
+    static constexpr bool kBulkMiss = false;
+    __device__ __forceinline__ bool bulk_miss(int, unsigned) { return false; }
+    __device__ __forceinline__ void finish(unsigned) {}
     RaySrc rays;
     int4* __restrict__ L;
     int* __restrict__ countL;
-    __device__ __forceinline__ void stage_issue(int base, unsigned char* buf, unsigned long long* mbar) const
+    __device__ __forceinline__ bool load(int i, d3& o, d3& d) const
     {
-        mbar_expect_tx(mbar, kStageBytes);
-        bulk_load(buf, rays.dir + 3 * (int64_t)base, 768, mbar);
-        if (PER_RAY_ORIGIN) bulk_load(buf + 768, rays.origin + 3 * (int64_t)base, 768, mbar);
-    }
-    __device__ __forceinline__ bool fetch(const unsigned char* buf, int j, int i, QRay& r) const
-    {
-        d3 o, d;
-        if (buf) {
-            d = ld3(reinterpret_cast<const double*>(buf) + 3 * j);
-            o = PER_RAY_ORIGIN ? ld3(reinterpret_cast<const double*>(buf + 768) + 3 * j) : rays.o(i);
-        } else {
-            o = rays.o(i);
-            d = rays.d(i);
-        }
-        r = cast_ray(o, d);
+        o = rays.o(i);
+        d = rays.d(i);
         return true;
     }
-    __device__ __forceinline__ void retire(int i, int id) const
+    __device__ __forceinline__ void retire(int i, int id, double) const
     {
         int slot = warp_append<>(countL, id >= 0);
         if (slot >= 0) L[slot] = make_int4(i, id, -1, 0);
     }
 };
 
-template <int MINB, bool PER_RAY_ORIGIN>
-__global__ void __launch_bounds__(128, MINB) ls_q1_kernel(BvhView B, LossEntryJob<PER_RAY_ORIGIN> job, int N,
-                                                          unsigned long long* work, int policy)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) ls_q1_kernel(BvhView B, LossEntryJob job, int N, unsigned long long* work, int policy)
 {
-    __shared__ WarpStage<LossEntryJob<PER_RAY_ORIGIN>::kStageBytes> stg[4];
-    staged_query<false>(B, job, N, work, policy, &stg[threadIdx.x >> 5]);
+    persistent_query<false>(B, job, N, work, policy);
 }
 
-// ---- R1: refraction at the entry hit, dense over L: float64 ray parked for R2, float32 copy for Q2 ----
+// ---- R1: refraction at the entry hit, dense over L, refracted ray parked at its slot ---------------
 __global__ void __launch_bounds__(128) ls_r1_kernel(BvhView B, const double* __restrict__ V64, RaySrc rays, double ext_ior,
                                                     double int_ior, int4* __restrict__ L, const int* __restrict__ countL,
-                                                    Park park, QPark qpark)
+                                                    Park park)
 {
     const int n = *countL;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -307,84 +134,72 @@ __global__ void __launch_bounds__(128) ls_r1_kernel(BvhView B, const double* __r
         d3 a0, a1, a2, o1, d1;
         load_tri64(B, V64, e.y, a0, a1, a2);
         hit_forward(h, rays.o(e.x), rays.d(e.x), a0, a1, a2, ext_ior, int_ior, o1, d1);
-        if (h.tir) {
-            L[k].w = 1;  // dead
-            qpark.store_dead(k);
-        } else {
-            park.store(k, o1, d1);
-            qpark.store(k, cast_ray(o1, d1));
-        }
+        if (h.tir) L[k].w = 1;  // dead
+        else park.store(k, o1, d1);
     }
 }
 
-// query over a float32 ray list (Q2 over L slots, Q3 over M slots)
-struct ListJobBase {
-    static constexpr int kStageBytes = 768;
-    QPark qp;
-    __device__ __forceinline__ void stage_issue(int base, unsigned char* buf, unsigned long long* mbar) const
-    {
-        mbar_expect_tx(mbar, 768);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) bulk_load(buf + 128 * c, qp.p + c * qp.cap + base, 128, mbar);
-    }
-    __device__ __forceinline__ bool fetch(const unsigned char* buf, int j, int k, QRay& r) const
-    {
-        if (buf) {
-            const float* f = reinterpret_cast<const float*>(buf);
-            r = QRay{f[j], f[32 + j], f[64 + j], f[96 + j], f[128 + j], f[160 + j]};
-        } else {
-            r = qp.load(k);
-        }
-        return r.ox == r.ox;  // NaN origin: dead slot
-    }
-};
-
 // ---- Q2: exit query over L -------------------------------------------------------------------------
-struct LossExitJob : ListJobBase {
+struct LossExitJob {
+    static constexpr bool kBulkMiss = false;
+    __device__ __forceinline__ bool bulk_miss(int, unsigned) { return false; }
+    __device__ __forceinline__ void finish(unsigned) {}
+    Park park;
     int4* __restrict__ L;
-    __device__ __forceinline__ void retire(int k, int id) const { L[k].z = id; }
+    __device__ __forceinline__ bool load(int k, d3& o, d3& d) const
+    {
+        if (L[k].w) return false;
+        park.load(k, o, d);
+        return true;
+    }
+    __device__ __forceinline__ void retire(int k, int id, double) const { L[k].z = id; }
 };
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) ls_q2_kernel(BvhView B, LossExitJob job, const int* __restrict__ countL,
                                                           unsigned long long* work, int policy)
 {
-    __shared__ WarpStage<768> stg[4];
-    staged_query<false>(B, job, *countL, work, policy, &stg[threadIdx.x >> 5]);
+    persistent_query<false>(B, job, *countL, work, policy);
 }
 
-// ---- R2: refraction at the exit hit; survivors appended to M (slot of L) with the float32 exit ray --------
+// ---- R2: refraction at the exit hit; exit ray parked in place, surviving SLOTS appended to M ---------
 __global__ void __launch_bounds__(128) ls_r2_kernel(BvhView B, const double* __restrict__ V64, double ext_ior, double int_ior,
                                                     const int4* __restrict__ L, const int* __restrict__ countL, Park park,
-                                                    int* __restrict__ M, int* __restrict__ countM, QPark qpark2)
+                                                    int* __restrict__ M, int* __restrict__ countM)
 {
     const int n = *countL;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const int4 e = L[k];
         bool alive = false;
-        d3 o2, d2;
         if (!e.w && e.z >= 0) {
             HitRec h;
-            d3 a0, a1, a2, o1, d1;
+            d3 a0, a1, a2, o1, d1, o2, d2;
             park.load(k, o1, d1);
             load_tri64(B, V64, e.z, a0, a1, a2);
             hit_forward(h, o1, d1, a0, a1, a2, ext_ior, int_ior, o2, d2);
             alive = !h.tir;
+            if (alive) park.store(k, o2, d2);
         }
         int slot = warp_append<>(countM, alive);
-        if (slot >= 0) {
-            M[slot] = k;
-            qpark2.store(slot, cast_ray(o2, d2));
-        }
+        if (slot >= 0) M[slot] = k;
     }
 }
 
-// ---- Q3: occlusion query over M; unoccluded slots of L appended to S -----------------------------------
-struct LossOcclusionJob : ListJobBase {
+// ---- Q3: occlusion query over M; unoccluded slots appended to S ---------------------------------------
+struct LossOcclusionJob {
+    static constexpr bool kBulkMiss = false;
+    __device__ __forceinline__ bool bulk_miss(int, unsigned) { return false; }
+    __device__ __forceinline__ void finish(unsigned) {}
+    Park park;
     const int* __restrict__ M;
     int* __restrict__ S;
     int* __restrict__ countS;
-    __device__ __forceinline__ void retire(int m, int id) const
+    __device__ __forceinline__ bool load(int m, d3& o, d3& d) const
+    {
+        park.load(M[m], o, d);
+        return true;
+    }
+    __device__ __forceinline__ void retire(int m, int id, double) const
     {
         int slot = warp_append<>(countS, id < 0);
         if (slot >= 0) S[slot] = M[m];
@@ -395,8 +210,7 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB) ls_q3_kernel(BvhView B, LossOcclusionJob job, const int* __restrict__ countM,
                                                           unsigned long long* work, int policy)
 {
-    __shared__ WarpStage<768> stg[4];
-    staged_query<true>(B, job, *countM, work, policy, &stg[threadIdx.x >> 5]);
+    persistent_query<true>(B, job, *countM, work, policy);
 }
 
 // ---- loss + backward over the valid paths -------------------------------------------------------------
