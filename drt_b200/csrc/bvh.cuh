@@ -32,11 +32,34 @@ namespace drt {
 // Triangle record, 80 B = 5 x double2, float64 so that the exact hit test needs no conversions:
 //   a.x a.y | a.z e1.x | e1.y e1.z | e2.x e2.y | e2.z id   (a = vertex 0, e1 = v1-v0, e2 = v2-v0, all
 //   computed in float64 from the float32 vertices, i.e. exactly what the query-stage test uses)
+//
+// Default layout (DRT_QNODE = 1): the same node QUANTISED to 32 B = 2 x uint4.  The traversal kernels are bound
+// by L1 data-pipe wavefronts of the divergent node fetches (ncu: l1tex__data_pipe_lsu_wavefronts 58-73 % of
+// peak, every other unit lower), and a 64-byte node costs four LDG.128 per lane per step; 32 bytes cost two
+// and halve the BVH footprint that L1/L2 have to hold.  Planes are 16-bit positions on a per-axis grid
+// spanning the root box, g0 + q * s with s = extent / 65520, stored OUTWARD (floor - 3 / ceil + 3 steps):
+//   q0 = (c0.x.lo | c0.x.hi << 16, c1.x.lo | c1.x.hi << 16, c0.y.., c1.y..)   q1 = (c0.z.., c1.z.., link0, link1)
+// The slab test stays one FFMA per plane, t = q * (s/d) + (g0 - o)/d (trace.cuh: node_step); the three
+// steps of margin cover the rounding of the quantisation (< 0.02 step) and of that FMA form (< 0.51 step for
+// origins within 64 extents of the grid, farther origins carry an additive slack), so a box test never
+// rejects a box that contains a true hit and hit ids stay bit-identical to the brute-force oracle.
+// scene[8..10] = g0, scene[11..13] = s (float bits), written by grid_kernel after the fit.
+#ifndef DRT_QNODE
+#define DRT_QNODE 1
+#endif
+#if DRT_QNODE
+constexpr int kNodeQuads = 2;
+typedef uint4 node_quad;
+#else
 constexpr int kNodeQuads = 4;
+typedef float4 node_quad;
+#endif
 constexpr int kTriD2 = 5;
+constexpr int kSceneWords = 16;
+constexpr float kGridSteps = 65520.f;  // steps across the root box; 7 spare steps on the low side, 8 on the high side
 
 struct BvhView {
-    const float4* nodes;
+    const node_quad* nodes;
     const double2* tris;
     const int32_t* F;      // [nF,3] original faces
     const unsigned* scene; // scene[7] = float bits of pmax
@@ -216,6 +239,60 @@ __device__ __forceinline__ float4 planes(float lo0, float hi0, float lo1, float 
     return make_float4(__fadd_rd(lo0, -infl), __fadd_ru(hi0, infl), __fadd_rd(lo1, -infl), __fadd_ru(hi1, infl));
 }
 
+// quantisation grid of the node planes from the root box (blo[0]/bhi[0]: node 0 is the root, or the only leaf)
+__global__ void grid_kernel(const float4* __restrict__ blo, const float4* __restrict__ bhi, unsigned* __restrict__ scene)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float4 l = blo[0], h = bhi[0];
+    float ext[3] = {__fadd_ru(h.x, -l.x), __fadd_ru(h.y, -l.y), __fadd_ru(h.z, -l.z)};
+    const float lo[3] = {l.x, l.y, l.z};
+    float emax = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
+    if (!(emax > 0.f)) emax = 1.f;  // a single point
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float e = fmaxf(ext[k], emax * 9.5367431640625e-07f);  // flat axis: keep a positive step (2^-20 of the largest extent)
+        const float s = __fdiv_ru(e, kGridSteps);
+        scene[8 + k] = __float_as_uint(__fadd_rd(lo[k], -__fmul_ru(7.f, s)));
+        scene[11 + k] = __float_as_uint(s);
+    }
+}
+
+#if DRT_QNODE
+__device__ __forceinline__ unsigned qpair(float lo, float hi, float g0, float inv_s)
+{
+    // outward: floor - 3 / ceil + 3 grid steps (the products are < 65536, their rounding error < 0.02 step)
+    const int ql = max(0, (int)floorf((lo - g0) * inv_s) - 3);
+    const int qh = min(65535, (int)ceilf((hi - g0) * inv_s) + 3);
+    return (unsigned)ql | ((unsigned)qh << 16);
+}
+
+__global__ void emit_nodes_kernel(int n, const int2* __restrict__ children, const float4* __restrict__ blo,
+                                  const float4* __restrict__ bhi, const unsigned* __restrict__ scene,
+                                  uint4* __restrict__ nodes)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float gx = __uint_as_float(scene[8]), gy = __uint_as_float(scene[9]), gz = __uint_as_float(scene[10]);
+    const float ix = __fdiv_rn(1.f, __uint_as_float(scene[11])), iy = __fdiv_rn(1.f, __uint_as_float(scene[12])),
+                iz = __fdiv_rn(1.f, __uint_as_float(scene[13]));
+    if (n == 1) {
+        if (i == 0) {  // single triangle: both slots are the one leaf (a duplicate test is harmless)
+            float4 l = blo[0], h = bhi[0];
+            const unsigned x = qpair(l.x, h.x, gx, ix), y = qpair(l.y, h.y, gy, iy), z = qpair(l.z, h.z, gz, iz);
+            nodes[0] = make_uint4(x, x, y, y);
+            nodes[1] = make_uint4(z, z, (unsigned)~0, (unsigned)~0);
+        }
+        return;
+    }
+    if (i >= n - 1) return;
+    int2 ch = children[i];
+    float4 l0 = blo[ch.x], h0 = bhi[ch.x], l1 = blo[ch.y], h1 = bhi[ch.y];
+    int c0 = ch.x >= n - 1 ? ~(ch.x - (n - 1)) : ch.x;
+    int c1 = ch.y >= n - 1 ? ~(ch.y - (n - 1)) : ch.y;
+    uint4* node = nodes + (size_t)i * kNodeQuads;
+    node[0] = make_uint4(qpair(l0.x, h0.x, gx, ix), qpair(l1.x, h1.x, gx, ix), qpair(l0.y, h0.y, gy, iy), qpair(l1.y, h1.y, gy, iy));
+    node[1] = make_uint4(qpair(l0.z, h0.z, gz, iz), qpair(l1.z, h1.z, gz, iz), (unsigned)c0, (unsigned)c1);
+}
+#else
 __global__ void emit_nodes_kernel(int n, const int2* __restrict__ children, const float4* __restrict__ blo,
                                   const float4* __restrict__ bhi, const unsigned* __restrict__ scene,
                                   float4* __restrict__ nodes)
@@ -243,6 +320,8 @@ __global__ void emit_nodes_kernel(int n, const int2* __restrict__ children, cons
     node[2] = planes(l0.z, h0.z, l1.z, h1.z, infl);
     node[3] = make_float4(__int_as_float(c0), __int_as_float(c1), 0.f, 0.f);
 }
+
+#endif  // DRT_QNODE
 
 __global__ void emit_tris_kernel(const int32_t* __restrict__ F, const float* __restrict__ V,
                                  const uint64_t* __restrict__ keys, int n, double2* __restrict__ tris)

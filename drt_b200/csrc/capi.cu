@@ -130,7 +130,7 @@ struct drt_bvh {
     int fused6_blocks_per_sm = 0;                // same for the 80-register variant
     uint64_t* sorted_keys = nullptr;             // the half of `keys` that holds the sorted (Morton, id) keys
     // traversal data
-    float4* nodes = nullptr;   size_t capN = 0;
+    node_quad* nodes = nullptr; size_t capN = 0;
     double2* tris = nullptr;   size_t capT = 0;
 
     BvhView view() const { return BvhView{nodes, tris, F, scene, nF}; }
@@ -177,6 +177,7 @@ int fit_and_emit(drt_bvh* b, cudaStream_t st)
     if (n > 1) CU(cudaMemsetAsync(b->flags, 0, sizeof(int) * (size_t)(n - 1), st));
     fit_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_keys, n, b->children, b->parent, b->blo, b->bhi,
                                                     b->flags); ++g_launches;
+    grid_kernel<<<1, 32, 0, st>>>(b->blo, b->bhi, b->scene); ++g_launches;
     emit_nodes_kernel<<<blocks_for(n > 1 ? n - 1 : 1, 256), 256, 0, st>>>(n, b->children, b->blo, b->bhi, b->scene, b->nodes); ++g_launches;
     emit_tris_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_keys, n, b->tris); ++g_launches;
     CU(cudaGetLastError());
@@ -275,8 +276,8 @@ int drt_bvh_create(int device, drt_bvh** out)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     b->sm_count = prop.multiProcessorCount;
-    CU(cudaMalloc(&b->scene, 8 * sizeof(unsigned)));
-    CU(cudaMemset(b->scene, 0, 8 * sizeof(unsigned)));
+    CU(cudaMalloc(&b->scene, kSceneWords * sizeof(unsigned)));
+    CU(cudaMemset(b->scene, 0, kSceneWords * sizeof(unsigned)));
     CU(cudaMalloc(&b->work, kWorkSlots * sizeof(unsigned long long)));
     if (tuning().prefer_l1) {
         // traversal kernels use < 1 KB of shared memory: ask for the largest L1 split explicitly
@@ -345,7 +346,7 @@ int drt_bvh_info(const drt_bvh* b, int64_t info[8])
     if (!b || !info) return fail(DRT_ERR_INVALID, "drt_bvh_info: null argument");
     info[0] = b->nF; info[1] = b->nV; info[2] = b->nF > 1 ? b->nF - 1 : (b->nF == 1 ? 1 : 0);
     info[3] = b->built ? 1 : 0;
-    info[4] = info[2] * (int64_t)(kNodeQuads * sizeof(float4));
+    info[4] = info[2] * (int64_t)(kNodeQuads * sizeof(node_quad));
     info[5] = (int64_t)b->nF * (int64_t)(kTriD2 * sizeof(double2));
     info[6] = b->builds; info[7] = b->refits;
     return DRT_OK;

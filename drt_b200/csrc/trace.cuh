@@ -36,11 +36,83 @@ __device__ __forceinline__ QRay cast_ray(d3 o, d3 d)
 // ---------------------------------------------------------------------------------------------
 struct RayQ {
     QRay r;
-    float ix, iy, iz;  // 1/d
-    float cx, cy, cz;  // o/d
-    float E;           // additive slack, 0 for origins within 64*pmax
+    float ix, iy, iz;  // 1/d            (quantised nodes: A = s/d, the grid step over the direction)
+    float cx, cy, cz;  // o/d            (quantised nodes: C' = (g0 - o)/d - 2^23 A, ADDED by the plane FFMA)
+    float E;           // additive slack, 0 for origins within 64*pmax (quantised: within 64 extents of the grid)
+#if DRT_QNODE
+    unsigned sx, sy, sz;  // PRMT selector of the NEAR plane of a (lo | hi << 16) pair on each axis
+#endif
 };
 
+#if DRT_QNODE
+// |d| < 2^-80 (including 0) is traced as +-2^-80: finite everywhere below (A 2^23 <= s 2^103), and such a ray moves
+// less than 2^-73 extents along that axis over any distance that matters -- far inside the plane margin.
+__device__ __forceinline__ float safe_inv(float d)
+{
+    return fabsf(d) < 8.271806125530277e-25f ? copysignf(1.2089258196146292e24f, d) : __fdiv_rn(1.f, d);
+}
+
+// Quantised planes p = g0 + q s:  t = (p - o)/d = q A + C with A = s/d, C = (g0 - o)/d.  q reaches the FFMA
+// without a conversion: PRMT glues the 16-bit q under the exponent of 2^23 (float bits 0x4B00qqqq = 2^23 + q,
+// exact), and the constant is folded into the addend, C' = C - 2^23 A.  The same PRMT picks the NEAR or the FAR
+// plane of the (lo | hi << 16) pair by the sign of A, so a node step costs 12 PRMT + 12 FFMA + 12 FMNMX -- the
+// instruction count of the float layout (12 FFMA + 24 FMNMX) with half the loads.
+// Error budget in grid steps, for origins within 64 extents of the grid: rounding of C' <= 0.5 (the same shift
+// for every plane of an axis), FMA-form terms |q A| 2^-24 + |C| 2^-23 <= 0.51, quantisation rounding < 0.02
+// (bvh.cuh: qpair) -- against 3 steps of outward margin on every stored plane.  Relative terms: the factor
+// 1 + 2^-20 on tfar.  Farther origins carry E = 2^-21 max(|C| + 2^23 |A|) >= the sum of both planes' errors.
+// Hence a box test never rejects a box that contains a true hit; the float64 triangle test decides every hit.
+__device__ __forceinline__ RayQ ray_setup(const BvhView& B, const QRay& r)
+{
+    RayQ q;
+    q.r = r;
+    const float inx = safe_inv(r.dx), iny = safe_inv(r.dy), inz = safe_inv(r.dz);
+    const float sx = __uint_as_float(__ldg(B.scene + 11)), sy = __uint_as_float(__ldg(B.scene + 12)), sz = __uint_as_float(__ldg(B.scene + 13));
+    const float wx = __uint_as_float(__ldg(B.scene + 8)) - r.ox, wy = __uint_as_float(__ldg(B.scene + 9)) - r.oy,
+                wz = __uint_as_float(__ldg(B.scene + 10)) - r.oz;
+    q.ix = sx * inx; q.iy = sy * iny; q.iz = sz * inz;
+    const float cx = wx * inx, cy = wy * iny, cz = wz * inz;
+    const float mx = 8388608.f * q.ix, my = 8388608.f * q.iy, mz = 8388608.f * q.iz;
+    q.cx = cx - mx; q.cy = cy - my; q.cz = cz - mz;
+    q.sx = inx >= 0.f ? 0x7410u : 0x7432u;
+    q.sy = iny >= 0.f ? 0x7410u : 0x7432u;
+    q.sz = inz >= 0.f ? 0x7410u : 0x7432u;
+    q.E = 0.f;
+    const float k = 64.f * 65520.f;
+    if (!(fabsf(wx) <= k * sx && fabsf(wy) <= k * sy && fabsf(wz) <= k * sz))
+        q.E = 4.76837158203125e-07f * fmaxf(fabsf(cx) + fabsf(mx), fmaxf(fabsf(cy) + fabsf(my), fabsf(cz) + fabsf(mz)));
+    return q;
+}
+
+__device__ __forceinline__ float qplane(unsigned w, unsigned sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
+
+// one binary node: test both children, continue with the nearer hit, push the other
+__device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float tmax, int node, int* stack, int& sp)
+{
+    const uint4* p = B.nodes + (size_t)node * kNodeQuads;
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    const unsigned fx = q.sx ^ 0x22u, fy = q.sy ^ 0x22u, fz = q.sz ^ 0x22u;  // selectors of the FAR planes
+    const float n0 = fmaxf(fmaxf(fmaf(qplane(a.x, q.sx), q.ix, q.cx), fmaf(qplane(a.z, q.sy), q.iy, q.cy)),
+                           fmaxf(fmaf(qplane(b.x, q.sz), q.iz, q.cz), 0.f));
+    const float f0 = fminf(fminf(fmaf(qplane(a.x, fx), q.ix, q.cx), fmaf(qplane(a.z, fy), q.iy, q.cy)),
+                           fminf(fmaf(qplane(b.x, fz), q.iz, q.cz), tmax));
+    const float n1 = fmaxf(fmaxf(fmaf(qplane(a.y, q.sx), q.ix, q.cx), fmaf(qplane(a.w, q.sy), q.iy, q.cy)),
+                           fmaxf(fmaf(qplane(b.y, q.sz), q.iz, q.cz), 0.f));
+    const float f1 = fminf(fminf(fmaf(qplane(a.y, fx), q.ix, q.cx), fmaf(qplane(a.w, fy), q.iy, q.cy)),
+                           fminf(fmaf(qplane(b.y, fz), q.iz, q.cz), tmax));
+    const bool h0 = n0 <= fmaf(f0, 1.00000095367431640625f, q.E);
+    const bool h1 = n1 <= fmaf(f1, 1.00000095367431640625f, q.E);
+    const int c0 = (int)b.z, c1 = (int)b.w;
+    if (h0 && h1) {
+        const bool first0 = n0 <= n1;
+        stack[sp++] = first0 ? c1 : c0;
+        return first0 ? c0 : c1;
+    }
+    if (h0) return c0;
+    if (h1) return c1;
+    return sp ? stack[--sp] : kDone;
+}
+#else
 __device__ __forceinline__ float safe_inv(float d)
 {
     return fabsf(d) < 7.888609052210118e-31f ? copysignf(1.2676506002282294e30f, d) : __fdiv_rn(1.f, d);
@@ -86,6 +158,7 @@ __device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float 
     if (h1) return c1;
     return sp ? stack[--sp] : kDone;
 }
+#endif
 
 // exact test of the one triangle of a leaf; updates the closest hit (ties -> lowest id)
 __device__ __forceinline__ bool leaf_step(const BvhView& B, const QRay& r, int leaf, double& t_best, int& id_best, float& tmax)
