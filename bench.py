@@ -252,7 +252,8 @@ def run_b200(args):
         if args.loss_path == "step":
             # public fused consumer (optim.py:91-108 + :210 as one autograd.Function = one library call): forward
             # wavefront, then loss + analytic backward over the valid paths; the library records marks[2] between them
-            loss = losses.ray_loss(scene, origins, d, targets=sparse, ev_after_fwd=marks[2].cuda_event if marks is not None else None)
+            loss = losses.ray_loss(scene, origins, d, targets=sparse, ev_after_fwd=marks[2].cuda_event if marks is not None else None,
+                                   image_size=(resy, resx))
             if marks is not None: marks[3].record()
             loss.backward()
             loss_buf.add_(loss.detach())
@@ -356,7 +357,7 @@ def run_b200(args):
             def compute(j, b):
                 o, d, scr, val = bufs[b]
                 if args.loss_path == "step":
-                    return losses.ray_loss(scene, o, d, screen=scr, valid=val)
+                    return losses.ray_loss(scene, o, d, screen=scr, valid=val, image_size=(resy, resx))
                 if args.loss_path == "rec":
                     return losses.ray_loss_rec(scene, o, d, scr, val)
                 out_ori, out_dir, mask = scene.render_transparent(o, d)
@@ -370,7 +371,7 @@ def run_b200(args):
             """the loader's lossless compact form (captured_data.CompactView): one origin row per pinhole view, ray_dir,
             sorted indices + screen points of the measured pixels only"""
             per_view = [CompactView.from_reference_view((view_slice(host[2], j), view_slice(host[3], j), None, view_slice(host[0], j),
-                                                         view_slice(host[1], j), None)) for j in range(len(cams))]
+                                                         view_slice(host[1], j), None), (resy, resx)) for j in range(len(cams))]
             ch = max(1, args.e2e_chunk)
             if any(c.origin.shape[0] != 1 for c in per_view):
                 ch = 1
@@ -395,7 +396,8 @@ def run_b200(args):
             def compute(j, b):
                 c, B = cvs[j], bufs[b]
                 nt, r, n = len(c.targets), c.origin.shape[0], c.ray_dir.shape[0]
-                return losses.ray_loss_view(scene, CompactView(B["o"][:r], B["d"][:n], losses.SparseTargets(B["idx"][:nt], B["xyz"][:nt])))
+                return losses.ray_loss_view(scene, CompactView(B["o"][:r], B["d"][:n], losses.SparseTargets(B["idx"][:nt], B["xyz"][:nt]),
+                                                               image_size=c.image_size))
             h2d = sum(c.h2d_bytes() for c in cvs)
             if world > 1:
                 t = torch.tensor([h2d], dtype=torch.float64, device=dev)
@@ -432,7 +434,7 @@ def run_b200(args):
                 for k in range(len(g)):
                     _lib.call("drt_generate_rays", resy, resx, p(Kinv), p(B["R"][k]), p(B["o"][k]), p(B["d"][k * n_pix:]), stream_ptr())
                 return losses.ray_loss_view(scene, CompactView(B["o"][:len(g)], B["d"][:len(g) * n_pix],
-                                                               losses.SparseTargets(B["idx"][:len(t)], B["xyz"][:len(t)])))
+                                                               losses.SparseTargets(B["idx"][:len(t)], B["xyz"][:len(t)]), image_size=(resy, resx)))
             h2d = sum(len(g) * 128 + len(t) * 28 for g, t in zip(groups, tg))
             return upload, compute, int(h2d), len(groups)
 

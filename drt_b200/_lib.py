@@ -26,8 +26,8 @@ SIGNATURES = {
     "drt_trace_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drt_ray_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "drt_ray_loss_grad_rec": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
-    "drt_ray_loss_step": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _f64, _f64, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp,
-                                    _vp, _vp, _vp]),
+    "drt_ray_loss_step": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _f64, _f64, C.c_int, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
+                                    _vp, _vp, _vp, _vp, _vp]),
     "drt_generate_rays": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
 }
 

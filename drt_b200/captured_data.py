@@ -49,18 +49,21 @@ class CompactView:
     pixels (captured_data.py:104: valid = screen_pixel[:,0] != 0).  73 B per ray of the reference layout become
     24 B + 28 B per MEASURED pixel; nothing is rounded."""
 
-    __slots__ = ("origin", "ray_dir", "targets", "mask", "camera_M")
+    __slots__ = ("origin", "ray_dir", "targets", "mask", "camera_M", "image_size")
 
-    def __init__(self, origin, ray_dir, targets, mask=None, camera_M=None):
+    def __init__(self, origin, ray_dir, targets, mask=None, camera_M=None, image_size=None):
         self.origin, self.ray_dir, self.targets, self.mask, self.camera_M = origin, ray_dir, targets, mask, camera_M
+        self.image_size = image_size  # (resy, resx) when the rays are whole scanline-ordered images (lets Q1 work on pixel tiles)
 
     @staticmethod
-    def from_reference_view(view):
+    def from_reference_view(view, image_size=None):
         """(screen_pixel, valid, mask, origin, ray_dir, camera_M) as captured_data.Data.Views holds it -> CompactView."""
         from .losses import SparseTargets
         screen, valid, mask, origin, ray_dir, cam = view
         one = origin.shape[0] > 0 and bool((origin == origin[:1]).all())
-        return CompactView(origin[:1].clone() if one else origin, ray_dir, SparseTargets.from_dense(screen, valid), mask, cam)
+        if image_size is not None and image_size[0] * image_size[1] != ray_dir.shape[0]:
+            image_size = None
+        return CompactView(origin[:1].clone() if one else origin, ray_dir, SparseTargets.from_dense(screen, valid), mask, cam, image_size)
 
     @staticmethod
     def concat(views):
@@ -72,18 +75,19 @@ class CompactView:
         if any(v.origin.shape[0] != 1 or v.ray_dir.shape[0] != n for v in views):
             raise ValueError("concat needs single-origin views of equal ray count")
         idx = torch.cat([v.targets.idx + k * n for k, v in enumerate(views)])
+        size = views[0].image_size if all(v.image_size == views[0].image_size for v in views) else None
         return CompactView(torch.cat([v.origin for v in views]), torch.cat([v.ray_dir for v in views]),
-                           SparseTargets(idx, torch.cat([v.targets.xyz for v in views])))
+                           SparseTargets(idx, torch.cat([v.targets.xyz for v in views])), image_size=size)
 
     def pin_memory(self):
         pin = lambda t: t.pin_memory() if torch.cuda.is_available() else t  # noqa: E731
         return CompactView(pin(self.origin), pin(self.ray_dir), self.targets.pin_memory() if torch.cuda.is_available()
-                           else self.targets, self.mask, self.camera_M)
+                           else self.targets, self.mask, self.camera_M, self.image_size)
 
     def to(self, device, non_blocking=True):
         up = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)  # noqa: E731
         cam = None if self.camera_M is None else tuple(up(m) for m in self.camera_M)
-        return CompactView(up(self.origin), up(self.ray_dir), self.targets.to(device, non_blocking), up(self.mask), cam)
+        return CompactView(up(self.origin), up(self.ray_dir), self.targets.to(device, non_blocking), up(self.mask), cam, self.image_size)
 
     def h2d_bytes(self):
         """bytes the ray path needs on the device (mask / camera_M belong to the silhouette path)"""
@@ -96,7 +100,8 @@ class CompactViews:
     def compact(self, V_index):
         cache = self.__dict__.setdefault("_compact", {})
         if V_index not in cache:
-            cache[V_index] = CompactView.from_reference_view(self.Views[V_index]).pin_memory()
+            size = (self.resy, self.resx) if hasattr(self, "resy") else None
+            cache[V_index] = CompactView.from_reference_view(self.Views[V_index], size).pin_memory()
         return cache[V_index]
 
     def get_view_compact(self, V_index):

@@ -54,6 +54,7 @@ struct Tuning {
     bool one_launch = false;  // DRT_ONE_LAUNCH=1: the cooperative single-launch variant (measured 1.5 % slower: spills)
     bool prefer_l1 = false;  // DRT_PREFER_L1=1 forces cudaSharedmemCarveoutMaxL1: measured 22 % SLOWER (the 1 KB/block reserve then caps residency at 4 blocks/SM)
     int bwd_merge = -1;  // DRT_BWD_MERGE = 0 | 1 forces the run-merged backward scatter off / on (default: by rays per vertex)
+    bool tile = true;  // DRT_TILE=0: keep scanline batches in drt_ray_loss_step even when the image size is known (A/B switch)
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
     int thresh = 32;
     int pol[3];  // make_policy(thresh, vote) of the three query stages: DRT_FWD_THRESH / DRT_VOTE, per stage DRT_THRESH_Q1.. / DRT_VOTE_Q1..
@@ -79,6 +80,8 @@ struct Tuning {
             if (c && atoi(c) >= 0 && atoi(c) <= 31) vo = atoi(c);
             pol[q] = make_policy(th, vo);
         }
+        const char* tl = getenv("DRT_TILE");
+        if (tl && !strcmp(tl, "0")) tile = false;
         const char* ol = getenv("DRT_ONE_LAUNCH");
         if (ol && !strcmp(ol, "1")) one_launch = true;
         const char* pl = getenv("DRT_PREFER_L1");
@@ -509,8 +512,8 @@ int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, const do
 
 int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin, int64_t rays_per_origin, const double* dir,
                       int64_t N, double ext_ior, double int_ior, int target_mode, const double* screen, const uint8_t* valid,
-                      const int32_t* tgt_idx, const double* tgt_xyz, int64_t n_tgt, double* loss_sum, double* grad_V,
-                      int32_t* n_paths, void* ev_after_fwd, void* stream)
+                      const int32_t* tgt_idx, const double* tgt_xyz, int64_t n_tgt, int32_t image_w, int32_t image_h,
+                      double* loss_sum, double* grad_V, int32_t* n_paths, void* ev_after_fwd, void* stream)
 {
     drt_bvh* b = const_cast<drt_bvh*>(b_);
     if (!b) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: null handle");
@@ -519,6 +522,7 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
     if (rays_per_origin < 1 || rays_per_origin > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: rays_per_origin must be >= 1");
     if (target_mode != 0 && target_mode != 1) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: target_mode must be 0 (dense) or 1 (sparse)");
     if (n_tgt < 0 || n_tgt > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: n_tgt must be in [0, 2^31)");
+    if (image_w < 0 || image_h < 0) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: negative image size");
     DeviceGuard g(b->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (n_paths) CU(cudaMemsetAsync(n_paths, 0, sizeof(int32_t), st));
@@ -561,7 +565,10 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
         else if (minb == 6) KERNEL<6><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
         else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
     } while (0)
-    LossEntryJob j1{rays, b->listA, countL};
+    // whole images of image_w x image_h pixels, both tileable by 8 x 4: a warp's batch becomes a pixel tile
+    const bool tile = tuning().tile && image_w > 0 && image_h > 0 && image_w % 8 == 0 && image_h % 4 == 0 &&
+                      (int64_t)image_w * image_h <= N && N % ((int64_t)image_w * image_h) == 0;
+    LossEntryJob j1{rays, b->listA, countL, tile ? image_w : 0, tile ? image_w * image_h : 0};
     DRT_LAUNCH_Q(ls_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
     ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park);
     LossExitJob j2{park, b->listA};

@@ -96,6 +96,11 @@ struct Park {
 };
 
 // ---- Q1: entry query over all rays; only hits leave a trace ---------------------------------------
+// Work item -> ray: rays arrive image by image in scanline order (captured_data.py:26-31), so 32 consecutive
+// rays are a 32 x 1 pixel strip.  When the caller passes the image size, a warp's batch is an 8 x 4 pixel TILE
+// instead: a tile is either inside or outside the silhouette far more often than a strip (the warp scheduling
+// model, tools/warp_sim, gives -22 % warp-wide steps for Q1 and -10 % for Q2/Q3, whose lists inherit the order),
+// and its rays share more of their node fetches.
 struct LossEntryJob {
     static constexpr bool kBulkMiss = false;
     __device__ __forceinline__ bool bulk_miss(int, unsigned) { return false; }
@@ -103,16 +108,26 @@ struct LossEntryJob {
     RaySrc rays;
     int4* __restrict__ L;
     int* __restrict__ countL;
-    __device__ __forceinline__ bool load(int i, d3& o, d3& d) const
+    int img_w, img_hw;  // image width and pixels per image; img_w = 0: no tiling
+    __device__ __forceinline__ int ray_of(int item) const
     {
+        if (!img_w) return item;
+        const int v = item / img_hw, r = item - v * img_hw;
+        const int t = r >> 5, w = r & 31, tpr = img_w >> 3;
+        const int ty = t / tpr, tx = t - ty * tpr;
+        return v * img_hw + (ty * 4 + (w >> 3)) * img_w + tx * 8 + (w & 7);
+    }
+    __device__ __forceinline__ bool load(int item, d3& o, d3& d) const
+    {
+        const int i = ray_of(item);
         o = rays.o(i);
         d = rays.d(i);
         return true;
     }
-    __device__ __forceinline__ void retire(int i, int id, double) const
+    __device__ __forceinline__ void retire(int item, int id, double) const
     {
         int slot = warp_append<>(countL, id >= 0);
-        if (slot >= 0) L[slot] = make_int4(i, id, -1, 0);
+        if (slot >= 0) L[slot] = make_int4(ray_of(item), id, -1, 0);
     }
 };
 

@@ -121,7 +121,7 @@ class RayLossStep(torch.autograd.Function):
     """loss and d loss/d vertices from ONE drt_ray_loss_step call (six launches, no dense per-ray output)."""
 
     @staticmethod
-    def forward(ctx, vertices, origin, rpo, ray_dir, screen, valid, targets, mesh, int_ior, ext_ior, n_paths, ev_after_fwd):
+    def forward(ctx, vertices, origin, rpo, ray_dir, screen, valid, targets, mesh, int_ior, ext_ior, n_paths, ev_after_fwd, image_size):
         dev = mesh.device
         V = vertices.detach().contiguous()
         o, d = origin.detach(), ray_dir.detach().contiguous()
@@ -149,7 +149,8 @@ class RayLossStep(torch.autograd.Function):
         loss = torch.zeros(1, dtype=torch.float64, device=dev)
         grad_V = torch.zeros_like(V) if need_grad else None
         _lib.call("drt_ray_loss_step", mesh._h, _ptr(V), _ptr(o), int(rpo), _ptr(d), n, float(ext_ior), float(int_ior), mode,
-                  _ptr(scr), _ptr(val), _ptr(idx), _ptr(xyz), n_tgt, _ptr(loss), _ptr(grad_V), _ptr(n_paths),
+                  _ptr(scr), _ptr(val), _ptr(idx), _ptr(xyz), n_tgt, int(image_size[1]) if image_size else 0,
+                  int(image_size[0]) if image_size else 0, _ptr(loss), _ptr(grad_V), _ptr(n_paths),
                   C.c_void_p(ev_after_fwd or 0), optix._stream_ptr(dev))
         st = torch.cuda.current_stream(dev)
         for t in (V, o, d, scr, val, idx, xyz):  # consumed asynchronously on the stream
@@ -161,22 +162,24 @@ class RayLossStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss):
         (grad_V,) = ctx.saved_tensors
-        return (grad_V * g_loss if grad_V is not None else None,) + (None,) * 11
+        return (grad_V * g_loss if grad_V is not None else None,) + (None,) * 12
 
 
-def ray_loss(scene, origin, ray_dir, screen=None, valid=None, targets=None, n_paths=None, ev_after_fwd=None):
+def ray_loss(scene, origin, ray_dir, screen=None, valid=None, targets=None, n_paths=None, ev_after_fwd=None, image_size=None):
     """sum over valid & traced rays of || out_dir - normalize(screen - out_ori) ||^2  (optim.py:96-106).
 
     Either the reference's dense pair (`screen` [N,3], `valid` [N] or None) or `targets` = SparseTargets.
     `origin`: [N,3], expanded/[1,3] (one origin for all rays) or [r,3] with r | N (ray i starts at row i // (N/r)).
-    `n_paths`: optional int32[1] device tensor receiving the number of valid two-bounce paths."""
+    `n_paths`: optional int32[1] device tensor receiving the number of valid two-bounce paths.
+    `image_size` = (resy, resx): optional hint that the rays are whole images in scanline order (captured_data.py:26-31);
+    the entry query then works on 8x4 pixel tiles.  Same results either way."""
     if (screen is None) == (targets is None):
         raise ValueError("give either screen (+valid) or targets")
     rows, rpo = origin_rows(origin, ray_dir.shape[0])
     return RayLossStep.apply(scene.vertices, rows, rpo, ray_dir, screen, valid, targets, scene.optix_mesh, _R.intIOR, _R.extIOR,
-                             n_paths, ev_after_fwd)
+                             n_paths, ev_after_fwd, image_size)
 
 
 def ray_loss_view(scene, view):
     """`view` = captured_data.CompactView (one origin row, ray_dir, sparse targets) on the scene's device."""
-    return ray_loss(scene, view.origin, view.ray_dir, targets=view.targets)
+    return ray_loss(scene, view.origin, view.ray_dir, targets=view.targets, image_size=getattr(view, "image_size", None))

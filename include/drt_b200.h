@@ -152,6 +152,10 @@ DRT_API int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, 
  *   target_mode 1   sparse targets: tgt_idx int32[n_tgt] = ray indices with a measured screen
  *                   point, strictly ascending, tgt_xyz float64[n_tgt,3]; every other ray is
  *                   `valid = False` (captured_data.py:104: valid = screen_pixel[:,0] != 0)
+ *   image_w/h       optional hint (0, 0 = none): the N rays are whole images of image_w x image_h pixels in
+ *                   scanline order (captured_data.py:26-31).  The entry query then walks 8 x 4 pixel tiles
+ *                   per warp instead of 32 x 1 strips (needs image_w % 8 == 0, image_h % 4 == 0 and
+ *                   N % (image_w * image_h) == 0, otherwise the hint is ignored).  Results do not depend on it.
  *   loss_sum        float64[1], ACCUMULATED into (caller zeroes)
  *   grad_V          float64[nV,3], ACCUMULATED into; NULL = loss value only
  *   n_paths         optional int32[1]: number of valid two-bounce paths of this batch (before the
@@ -162,8 +166,8 @@ DRT_API int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, 
  */
 DRT_API int drt_ray_loss_step(const drt_bvh* bvh, const double* V64, const double* origin, int64_t rays_per_origin,
                       const double* dir, int64_t N, double ext_ior, double int_ior, int target_mode, const double* screen,
-                      const uint8_t* valid, const int32_t* tgt_idx, const double* tgt_xyz, int64_t n_tgt, double* loss_sum,
-                      double* grad_V, int32_t* n_paths, void* ev_after_fwd, void* stream);
+                      const uint8_t* valid, const int32_t* tgt_idx, const double* tgt_xyz, int64_t n_tgt, int32_t image_w,
+                      int32_t image_h, double* loss_sum, double* grad_V, int32_t* n_paths, void* ev_after_fwd, void* stream);
 
 /*
  * Replaces captured_data.generate_ray -- captured_data.py:23-40 (the pinhole sets build their rays

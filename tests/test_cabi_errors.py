@@ -30,7 +30,7 @@ def test_null_and_range_arguments_cpu():
     assert lib.drt_trace_bwd(None, None, None, None, 0, 1.0, 1.5, None, None, None, None, None, None) == 1
     assert lib.drt_ray_loss_grad(None, None, None, None, None, -1, None, None, None) == 1 and "N < 0" in _err()
     assert lib.drt_ray_loss_grad(None, None, None, None, None, 0, None, None, None) == 0
-    assert lib.drt_ray_loss_step(None, None, None, 1, None, 0, 1.0, 1.5, 0, None, None, None, None, 0, None, None, None, None, None) == 1
+    assert lib.drt_ray_loss_step(None, None, None, 1, None, 0, 1.0, 1.5, 0, None, None, None, None, 0, 0, 0, None, None, None, None, None) == 1
     assert "null handle" in _err()
     assert lib.drt_generate_rays(4, 4, None, None, None, None, None) == 1 and "null buffer" in _err()
     assert lib.drt_kernel_launches() >= 0

@@ -56,7 +56,7 @@ def _targets(sc, o, d, seed, keep=0.8):
     return screen, valid, mk
 
 
-@pytest.mark.parametrize("mesh,res,ks", [("hand_vh", (96, 128), (11,)), ("mouse_vh", (120, 100), (3, 40, 57))])
+@pytest.mark.parametrize("mesh,res,ks", [("hand_vh", (96, 128), (11,)), ("mouse_vh", (120, 104), (3, 40, 57))])
 def test_loss_step_vs_oracle_and_every_input_layout(cuda_device, mesh, res, ks):
     from drt_b200 import losses
     v, f = load_mesh(mesh)
@@ -83,6 +83,10 @@ def test_loss_step_vs_oracle_and_every_input_layout(cuda_device, mesh, res, ks):
         "sparse targets, origin per ray": run(o, targets=sparse),
         "sparse targets, origin per view": run(per_view, targets=sparse),
         "dense targets, origin per view": run(per_view, screen=screen, valid=valid),
+        # image size known: the entry query walks 8x4 pixel tiles instead of 32x1 strips -- same paths, same numbers
+        "tiles, sparse targets, origin per view": run(per_view, targets=sparse, image_size=res),
+        "tiles, dense targets, origin per ray": run(o, screen=screen, valid=valid, image_size=res),
+        "untileable image size hint is ignored": run(per_view, targets=sparse, image_size=(res[0] + 1, res[1])),
     }
     if len(ks) == 1:
         layouts["expanded origin"] = run(per_view.expand(len(d), 3), targets=sparse)
@@ -222,11 +226,11 @@ def test_loss_step_cabi_errors(cuda_device):
     V = sc.vertices.detach()
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     err = lambda: lib.drt_last_error().decode()  # noqa: E731
-    assert lib.drt_ray_loss_step(h, p(V), p(t), 0, p(t), 8, 1.0, 1.5, 0, p(t), None, None, None, 0, p(t), None, None, None, st) == 1 and "rays_per_origin" in err()
-    assert lib.drt_ray_loss_step(h, p(V), p(t), 1, p(t), 8, 1.0, 1.5, 2, p(t), None, None, None, 0, p(t), None, None, None, st) == 1 and "target_mode" in err()
-    assert lib.drt_ray_loss_step(h, p(V), p(t), 1, p(t), 8, 1.0, 1.5, 0, None, None, None, None, 0, p(t), None, None, None, st) == 1 and "screen" in err()
-    assert lib.drt_ray_loss_step(h, p(V), p(t), 1, p(t), 8, 1.0, 1.5, 1, None, None, None, None, 3, p(t), None, None, None, st) == 1 and "sparse" in err()
-    assert lib.drt_ray_loss_step(h, p(V), p(t), 1, p(t), 8, 1.0, 1.5, 0, p(t), None, None, None, 0, None, None, None, None, st) == 1
-    assert lib.drt_ray_loss_step(h, p(V), p(t), 1, p(t), 8, 1.0, 1.5, 0, p(t), None, None, None, 0, p(t), None, None, None, st) == 0
+    assert lib.drt_ray_loss_step(h, p(V), p(t), 0, p(t), 8, 1.0, 1.5, 0, p(t), None, None, None, 0, 0, 0, p(t), None, None, None, st) == 1 and "rays_per_origin" in err()
+    assert lib.drt_ray_loss_step(h, p(V), p(t), 1, p(t), 8, 1.0, 1.5, 2, p(t), None, None, None, 0, 0, 0, p(t), None, None, None, st) == 1 and "target_mode" in err()
+    assert lib.drt_ray_loss_step(h, p(V), p(t), 1, p(t), 8, 1.0, 1.5, 0, None, None, None, None, 0, 0, 0, p(t), None, None, None, st) == 1 and "screen" in err()
+    assert lib.drt_ray_loss_step(h, p(V), p(t), 1, p(t), 8, 1.0, 1.5, 1, None, None, None, None, 3, 0, 0, p(t), None, None, None, st) == 1 and "sparse" in err()
+    assert lib.drt_ray_loss_step(h, p(V), p(t), 1, p(t), 8, 1.0, 1.5, 0, p(t), None, None, None, 0, 0, 0, None, None, None, None, st) == 1
+    assert lib.drt_ray_loss_step(h, p(V), p(t), 1, p(t), 8, 1.0, 1.5, 0, p(t), None, None, None, 0, 0, 0, p(t), None, None, None, st) == 0
     assert lib.drt_generate_rays(-1, 4, p(t), p(t), p(t), p(t), st) == 1
     torch.cuda.synchronize()

@@ -58,8 +58,22 @@ def refract(o, d, tri, ext=1.00029, inn=configs.INT_IOR):
     return x + 1e-5 * wt, wt, ~tir
 
 
+TILE = os.environ.get("TILE")   # e.g. "8x4": reorder every view into tiles of 32 pixels (x fastest inside the tile)
+
+
+def tile_order(resy, resx, tw, th):
+    ys, xs = np.meshgrid(np.arange(resy), np.arange(resx), indexing="ij")
+    key = ((ys // th) * (resx // tw) + xs // tw) * (tw * th) + (ys % th) * tw + xs % tw
+    return np.argsort(key.reshape(-1), kind="stable")
+
+
 o = np.concatenate([views.generate_ray(cfg["resy"], cfg["resx"], cfg["cams"][k][3], cfg["cams"][k][2])[0].numpy() for k in view_ids])
 d = np.concatenate([views.generate_ray(cfg["resy"], cfg["resx"], cfg["cams"][k][3], cfg["cams"][k][2])[1].numpy() for k in view_ids])
+if TILE:
+    tw, th = (int(x) for x in TILE.split("x"))
+    n_pix = cfg["resy"] * cfg["resx"]
+    perm = np.concatenate([k * n_pix + tile_order(cfg["resy"], cfg["resx"], tw, th) for k in range(len(view_ids))])
+    o, d = o[perm], d[perm]
 write_rays(f"{out}/q1.bin", o, d)
 id1, _ = hits(f"{out}/q1.bin")
 h = id1 >= 0

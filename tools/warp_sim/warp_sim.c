@@ -253,6 +253,7 @@ int main(int argc, char** argv)
     stats S0 = run(n, &base, warps, hid, ht);
     if (argc > 4) { FILE* f = fopen(argv[4], "wb"); fwrite(hid, sizeof(int), n, f); fwrite(ht, sizeof(double), n, f); fclose(f); }
     if (getenv("SIM_HITS_ONLY")) return 0;
+    if (getenv("SIM_BASE_ONLY")) { printf("hit fraction %.3f, node steps per ray %.1f\n", (double)S0.hits / S0.rays, S0.node_lane_steps / S0.rays); report("kernel today: defer 2, refill 32, sync drain", &S0, NULL); return 0; }
     printf("hit fraction %.3f, node steps per ray %.1f, leaf tests per ray %.2f\n", (double)S0.hits / S0.rays, S0.node_lane_steps / S0.rays, S0.leaf_lane_tests / S0.rays);
     report("kernel today: defer 2, refill 32, sync drain", &S0, NULL);
     int defers[] = {1, 4, 8};
