@@ -180,13 +180,15 @@ __device__ __forceinline__ bool leaf_step(const BvhView& B, const QRay& r, int l
 
 // Leaves are DEFERRED: a lane that reaches a leaf parks it in a small per-lane queue (kept at the
 // top end of its stack array) and keeps walking internal nodes; the exact triangle tests run in
-// batches once kDefer (= 2; 1, 4 and 8 measured slower) leaves are queued or the walk is over.  Measured on B200 with test-at-once
-// traversal, a warp entered the (long, float64) leaf phase every ~1.5 node steps with ~2 of 32
+// batches once kDefer leaves are queued or the walk is over.  Measured motivation on B200 with test-at-once
+// traversal: a warp entered the (long, float64) leaf phase every ~1.5 node steps with ~2 of 32
 // lanes active -- every lane parked at a leaf stalls until the slowest lane reaches one.  Deferral
 // costs some closest-hit pruning (tmax is updated a few nodes later), never correctness: every leaf
 // whose box passed the test is still tested, and ties still resolve to the lowest id.
+// Depth: with every lane filling its own queue (walk) 2 was best (1: -9 %, 4: -1 %, 8: -6 % at C4); with the
+// warp vote (walk_vote) 3 is (C4 forward 6.43 ms at 3 vs 6.55 at 2 and 6.47 at 4, vote 8).
 #ifndef DRT_DEFER
-#define DRT_DEFER 2
+#define DRT_DEFER 3
 #endif
 constexpr int kDefer = DRT_DEFER;
 
