@@ -219,6 +219,7 @@ def run_b200(args):
     n_total = n_views * n_pix
 
     R.intIOR = configs.INT_IOR
+    R.resy, R.resx = resy, resx      # optim.py:179-180 (render_transparent passes it on as the tile hint)
     scene = R.Scene(vertices=cfg["vertices"], faces=cfg["faces"], cuda_device=local)
     scene.refit = bool(args.refit)
     V = scene.vertices.clone().requires_grad_(True)

@@ -157,6 +157,7 @@ class Scene:
 
     # DiffRender.py:420-432
     def render_transparent(self, origin, ray_dir):
+        self.optix_mesh.set_image_size(resy, resx)  # module globals, assigned by the caller like optim.py:179-180
         return RefractTrace.apply(self.vertices, origin, ray_dir, self.optix_mesh, intIOR, extIOR)
 
     # DiffRender.py:434-438

@@ -131,6 +131,8 @@ struct drt_bvh {
     int work_slot = 0;
     int fused_blocks_per_sm = 0;                 // co-resident blocks of wf_fused_kernel<8> (0: no cooperative launch)
     int fused6_blocks_per_sm = 0;                // same for the 80-register variant
+    int img_w = 0, img_h = 0;                    // drt_bvh_set_image_size: rays of drt_trace_fwd are whole scanline images
+    int bwd_blocks[3] = {8, 3, 3};               // co-resident blocks per SM of ls_loss_bwd_kernel<loss only | grad | grad+merge>
     uint64_t* sorted_keys = nullptr;             // the half of `keys` that holds the sorted (Morton, id) keys
     // traversal data
     node_quad* nodes = nullptr; size_t capN = 0;
@@ -155,6 +157,14 @@ struct DeviceGuard {
         if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
     }
 };
+
+// 8 x 4 pixel tiles are possible when the N rays are whole images whose sides the tile divides
+TileMap tile_map(int img_w, int img_h, int64_t N)
+{
+    const bool ok = tuning().tile && img_w > 0 && img_h > 0 && img_w % 8 == 0 && img_h % 4 == 0 && (int64_t)img_w * img_h <= N &&
+                    N % ((int64_t)img_w * img_h) == 0;
+    return ok ? TileMap{img_w, img_w * img_h} : TileMap{0, 0};
+}
 
 // clamp + count out-of-range indices so that no later kernel can fault on a bad face list
 __global__ void copy_faces_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n3, int nV, int* __restrict__ bad)
@@ -301,6 +311,9 @@ int drt_bvh_create(int device, drt_bvh** out)
         if (coop) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->fused6_blocks_per_sm, wf_fused_kernel<6>, 128, 0));
     }
 
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[0], ls_loss_bwd_kernel<false, false>, 128, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[1], ls_loss_bwd_kernel<true, false>, 128, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[2], ls_loss_bwd_kernel<true, true>, 128, 0));
     *out = b;
     return DRT_OK;
 }
@@ -342,6 +355,15 @@ int drt_bvh_update_vert(drt_bvh* b, const float* V32, const double* V64, int32_t
     if ((rc = set_vertices(b, V32, V64, nV, st))) return rc;
     if (refit) { b->refits++; return fit_and_emit(b, st); }
     return build_tree(b, st);
+}
+
+int drt_bvh_set_image_size(drt_bvh* b, int32_t image_w, int32_t image_h)
+{
+    if (!b) return fail(DRT_ERR_INVALID, "drt_bvh_set_image_size: null handle");
+    if (image_w < 0 || image_h < 0) return fail(DRT_ERR_INVALID, "drt_bvh_set_image_size: negative size");
+    b->img_w = image_w;
+    b->img_h = image_h;
+    return DRT_OK;
 }
 
 int drt_bvh_info(const drt_bvh* b, int64_t info[8])
@@ -400,7 +422,7 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
     if (tuning().simple_fwd || (!tuning().force_wavefront && N <= kSimpleMaxRays)) {
         int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
         trace_fwd_kernel<<<grid, 128, 0, st>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir, mask3,
-                                               (int4*)rec, rec_count, hit1);
+                                               (int4*)rec, rec_count, hit1, tile_map(b->img_w, b->img_h, N));
     } else {
         // production path: wavefront of persistent query kernels (wavefront.cuh)
         int rc;
@@ -415,13 +437,14 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
         // bulk zero-fill needs 16-byte aligned output rows for every multiple-of-32 ray index
         const bool bulk_ok = tuning().bulk && !(((uintptr_t)out_ori | (uintptr_t)out_dir | (uintptr_t)mask3 | (uintptr_t)hit1) & 15u);
         const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
-        EntryJob j1{bulk_ok ? reinterpret_cast<const ZeroTile*>(1) : nullptr, false, origin, dir, out_ori, out_dir, mask3, hit1, b->listA, countL};
+        EntryJob j1{bulk_ok ? reinterpret_cast<const ZeroTile*>(1) : nullptr, false, origin, dir, out_ori, out_dir, mask3, hit1, b->listA, countL,
+                    tile_map(b->img_w, b->img_h, N)};
         const int minb = tuning().minb;
         const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
         if (tuning().one_launch && b->fused_blocks_per_sm > 0) {
             // the whole wavefront as ONE cooperative launch (grid-wide barriers between the stages)
             FwdArgs fa{b->view(), V64, origin, dir, (int)N, ext_ior, int_ior, out_ori, out_dir, mask3, hit1, b->listA, b->listB,
-                       (int4*)rec, rec_count, ctl, {pol[0], pol[1], pol[2]}, bulk_ok ? 1 : 0};
+                       (int4*)rec, rec_count, ctl, {pol[0], pol[1], pol[2]}, bulk_ok ? 1 : 0, tile_map(b->img_w, b->img_h, N)};
             void* kargs[] = {&fa};
             const bool six = minb == 6 && b->fused6_blocks_per_sm > 0;
             const int per_sm = six ? b->fused6_blocks_per_sm : b->fused_blocks_per_sm;
@@ -566,9 +589,7 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
         else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
     } while (0)
     // whole images of image_w x image_h pixels, both tileable by 8 x 4: a warp's batch becomes a pixel tile
-    const bool tile = tuning().tile && image_w > 0 && image_h > 0 && image_w % 8 == 0 && image_h % 4 == 0 &&
-                      (int64_t)image_w * image_h <= N && N % ((int64_t)image_w * image_h) == 0;
-    LossEntryJob j1{rays, b->listA, countL, tile ? image_w : 0, tile ? image_w * image_h : 0};
+    LossEntryJob j1{rays, b->listA, countL, tile_map(image_w, image_h, N)};
     DRT_LAUNCH_Q(ls_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
     ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park);
     LossExitJob j2{park, b->listA};
@@ -579,12 +600,14 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
 #undef DRT_LAUNCH_Q
     if (ev_after_fwd) CU(cudaEventRecord((cudaEvent_t)ev_after_fwd, st));
     const bool merge = tuning().bwd_merge == 1 || (tuning().bwd_merge < 0 && N / std::max(b->nV, 1) > 5000);
+    // grid = what is co-resident (the kernel is register-bound at 3-4 blocks per SM): a larger grid-stride grid only adds a ragged last wave
+    const int bgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * std::max(1, grad_V ? (merge ? b->bwd_blocks[2] : b->bwd_blocks[1]) : b->bwd_blocks[0]));
     if (!grad_V)
-        ls_loss_bwd_kernel<false, false><<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, nullptr);
+        ls_loss_bwd_kernel<false, false><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, nullptr);
     else if (merge)
-        ls_loss_bwd_kernel<true, true><<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
+        ls_loss_bwd_kernel<true, true><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
     else
-        ls_loss_bwd_kernel<true, false><<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
+        ls_loss_bwd_kernel<true, false><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
     g_launches += 6;
     CU(cudaGetLastError());
     if (n_paths) CU(cudaMemcpyAsync(n_paths, countS, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));

@@ -96,11 +96,8 @@ struct Park {
 };
 
 // ---- Q1: entry query over all rays; only hits leave a trace ---------------------------------------
-// Work item -> ray: rays arrive image by image in scanline order (captured_data.py:26-31), so 32 consecutive
-// rays are a 32 x 1 pixel strip.  When the caller passes the image size, a warp's batch is an 8 x 4 pixel TILE
-// instead: a tile is either inside or outside the silhouette far more often than a strip (the warp scheduling
-// model, tools/warp_sim, gives -22 % warp-wide steps for Q1 and -10 % for Q2/Q3, whose lists inherit the order),
-// and its rays share more of their node fetches.
+// Work item -> ray through TileMap (trace.cuh): with the image size known a warp's batch is an 8 x 4 pixel tile
+// (the warp scheduling model, tools/warp_sim, gives -22 % warp-wide steps for Q1 and -10 % for Q2/Q3).
 struct LossEntryJob {
     static constexpr bool kBulkMiss = false;
     __device__ __forceinline__ bool bulk_miss(int, unsigned) { return false; }
@@ -108,15 +105,8 @@ struct LossEntryJob {
     RaySrc rays;
     int4* __restrict__ L;
     int* __restrict__ countL;
-    int img_w, img_hw;  // image width and pixels per image; img_w = 0: no tiling
-    __device__ __forceinline__ int ray_of(int item) const
-    {
-        if (!img_w) return item;
-        const int v = item / img_hw, r = item - v * img_hw;
-        const int t = r >> 5, w = r & 31, tpr = img_w >> 3;
-        const int ty = t / tpr, tx = t - ty * tpr;
-        return v * img_hw + (ty * 4 + (w >> 3)) * img_w + tx * 8 + (w & 7);
-    }
+    TileMap tiles;
+    __device__ __forceinline__ int ray_of(int item) const { return tiles.ray_of(item); }
     __device__ __forceinline__ bool load(int item, d3& o, d3& d) const
     {
         const int i = ray_of(item);
@@ -233,8 +223,11 @@ __global__ void __launch_bounds__(128, MINB) ls_q3_kernel(BvhView B, LossOcclusi
 //   target = normalize(screen - out_ori),  diff = out_dir - target,  loss += |diff|^2,  g_out_dir = 2 diff
 // (optim.py:99-106; out_ori is detached, optim.py:100, so g_out_ori = 0) and runs the analytic reverse
 // of the chain (common.cuh:hit_backward) into grad_V.  GRAD = false: loss value only.
+#ifndef DRT_BWD_MINB
+#define DRT_BWD_MINB 3
+#endif
 template <bool GRAD, bool MERGE>
-__global__ void __launch_bounds__(128, 3) ls_loss_bwd_kernel(BvhView B, const double* __restrict__ V64, RaySrc rays,
+__global__ void __launch_bounds__(128, DRT_BWD_MINB) ls_loss_bwd_kernel(BvhView B, const double* __restrict__ V64, RaySrc rays,
                                                              double ext_ior, double int_ior, const int4* __restrict__ L,
                                                              const int* __restrict__ S, const int* __restrict__ countS,
                                                              TargetSrc tgt, double* __restrict__ loss_sum,

@@ -143,14 +143,17 @@ struct EntryJob {
     uint8_t* __restrict__ hit1;
     int4* __restrict__ L;
     int* __restrict__ countL;
-    __device__ __forceinline__ bool load(int i, d3& o, d3& d) const
+    TileMap tiles;  // work item -> ray (8 x 4 pixel tiles when the image size is known)
+    __device__ __forceinline__ bool load(int item, d3& o, d3& d) const
     {
+        const int i = tiles.ray_of(item);
         o = ld3(origin + 3 * (int64_t)i);
         d = ld3(dir + 3 * (int64_t)i);
         return true;
     }
-    __device__ __forceinline__ void retire(int i, int id, double) const
+    __device__ __forceinline__ void retire(int item, int id, double) const
     {
+        const int i = tiles.ray_of(item);
         if (hit1) hit1[i] = id >= 0 ? 1 : 0;
         if (id < 0) write_invalid(out_ori, out_dir, mask3, i);
         int slot = warp_append<>(countL, id >= 0);
@@ -160,7 +163,7 @@ struct EntryJob {
     // (87 % of the primary rays of the benchmark views miss; per-lane this would be 10 strided stores each)
     __device__ __forceinline__ bool bulk_miss(int first, unsigned lane)
     {
-        if (!zeros) return false;
+        if (!zeros || tiles.img_w) return false;  // a tile's rows are four separate runs: plain stores
         if (lane == 0) {
             bulk_store(out_ori + 3 * (int64_t)first, zeros->z, 768);
             bulk_store(out_dir + 3 * (int64_t)first, zeros->z, 768);
@@ -349,6 +352,7 @@ struct FwdArgs {
     unsigned long long* ctl;  // [0..2] work counters of Q1,Q2,Q3; [3] = {countL, countM}
     int policy[3];  // make_policy(thresh, vote) of Q1, Q2, Q3
     int bulk;
+    TileMap tiles;
 };
 
 template <int MINB>
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(128, MINB) wf_fused_kernel(FwdArgs a)
     int* countL = reinterpret_cast<int*>(a.ctl + 3);
     int* countM = countL + 1;
     {
-        EntryJob j{a.bulk ? &zt : nullptr, false, a.origin, a.dir, a.out_ori, a.out_dir, a.mask3, a.hit1, a.L, countL};
+        EntryJob j{a.bulk ? &zt : nullptr, false, a.origin, a.dir, a.out_ori, a.out_dir, a.mask3, a.hit1, a.L, countL, a.tiles};
         persistent_query<false>(a.B, j, a.N, a.ctl + 0, a.policy[0]);
     }
     grid.sync();

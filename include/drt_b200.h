@@ -62,6 +62,15 @@ DRT_API int drt_bvh_build_f64(drt_bvh* bvh, const int32_t* F, int32_t nF, const 
  */
 DRT_API int drt_bvh_update_vert(drt_bvh* bvh, const float* V32, const double* V64, int32_t nV, int refit, void* stream);
 
+/*
+ * The reference keeps the render resolution in module globals (DiffRender.py:16-17 `resy`, `resx`, assigned
+ * by optim.py:179-180); this is their counterpart on the handle.  It is a HINT: when the N rays of a later
+ * drt_trace_fwd call are whole images of image_w x image_h pixels in scanline order (N % (w*h) == 0,
+ * w % 8 == 0, h % 4 == 0) the entry query walks 8 x 4 pixel tiles per warp instead of 32 x 1 strips.
+ * Results do not depend on it.  (0, 0) clears the hint.  Host call, no device work.
+ */
+DRT_API int drt_bvh_set_image_size(drt_bvh* bvh, int32_t image_w, int32_t image_h);
+
 /* Number of face indices that were outside [0,nV) at the last drt_bvh_build (they are clamped so
  * that no kernel faults; the reference would read out of bounds).  Synchronises `stream`. */
 DRT_API int drt_bvh_bad_indices(const drt_bvh* bvh, void* stream, int* out);

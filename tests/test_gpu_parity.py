@@ -283,3 +283,32 @@ def test_fused_ray_loss_matches_reference_expression(cuda_device):
     assert abs(mine.item() - ref.item()) <= 1e-12 * abs(ref.item())
     pv, gl = grad_rel_err(Vb.grad.cpu().numpy(), Va.grad.cpu().numpy())
     assert pv < 1e-10 and gl < 1e-12, (pv, gl)
+
+
+@pytest.mark.parametrize("res", [(96, 128), (1100, 1200)])
+def test_image_size_hint_changes_nothing_but_the_batching(cuda_device, res):
+    """Render.resy / resx (DiffRender.py:16-17, optim.py:179-180) let the entry query walk 8x4 pixel tiles: outputs,
+    masks and gradients are those of the scanline batching (small batch: one-launch kernel, large: wavefront)."""
+    from drt_b200 import views
+    v, f = load_mesh("mouse_vh")
+    R, sc = _scene(v, f, cuda_device)
+    cam = views.turntable_cameras(v, res[0], res[1], 72)[31]
+    o, d = views.generate_ray(res[0], res[1], cam[3], cam[2], device=cuda_device)
+    g = torch.randn(o.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(2)).to(cuda_device)
+    outs = []
+    old = (R.resy, R.resx)
+    try:
+        for hint in ((res[0] + 1, res[1]), res):       # first an untileable size (ignored), then the real one
+            R.resy, R.resx = hint
+            V = sc.vertices.detach().clone().requires_grad_(True)
+            sc.update_verticex(V)
+            oo, od, mk = sc.render_transparent(o, d)
+            (od * g).sum().backward()
+            outs.append((oo.detach().clone(), od.detach().clone(), mk.clone(), V.grad.clone(), sc.render_mask(o, d)))
+    finally:
+        R.resy, R.resx = old
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[4], b[4])
+    assert a[2].any()
+    pv, gl = grad_rel_err(b[3].cpu().numpy(), a[3].cpu().numpy())
+    assert pv < 1e-10 and gl < 1e-12, (pv, gl)
