@@ -223,9 +223,6 @@ __global__ void __launch_bounds__(128, MINB) ls_q3_kernel(BvhView B, LossOcclusi
 //   target = normalize(screen - out_ori),  diff = out_dir - target,  loss += |diff|^2,  g_out_dir = 2 diff
 // (optim.py:99-106; out_ori is detached, optim.py:100, so g_out_ori = 0) and runs the analytic reverse
 // of the chain (common.cuh:hit_backward) into grad_V.  GRAD = false: loss value only.
-#ifndef DRT_BWD_MINB
-#define DRT_BWD_MINB 3
-#endif
 template <bool GRAD, bool MERGE>
 __global__ void __launch_bounds__(128, DRT_BWD_MINB) ls_loss_bwd_kernel(BvhView B, const double* __restrict__ V64, RaySrc rays,
                                                              double ext_ior, double int_ior, const int4* __restrict__ L,

@@ -419,8 +419,13 @@ __device__ __forceinline__ void scatter_runs(double* __restrict__ gV, const int3
 // MERGE = true merges the atomics of equal-triangle runs first (scatter_runs): measured 1.28 -> 0.85 ms at C3
 // (4 625 vertices take 95 M float64 atomics: contention-bound) but 0.56 -> 0.62 ms at C4 (25 126 vertices), so
 // the host picks it by rays per vertex.
+// Launch bound: 4 blocks per SM (128 registers, a few spills) beats 3 (154 registers): the kernel is latency-bound
+// on its gathers and atomics, so residency wins -- ls_loss_bwd_kernel measured 0.65 ms at 3, 0.57 ms at 4, 0.65 at 2 (C4).
+#ifndef DRT_BWD_MINB
+#define DRT_BWD_MINB 4
+#endif
 template <bool MERGE>
-__global__ void __launch_bounds__(128, 3) trace_bwd_kernel(BvhView B, const double* __restrict__ V64,
+__global__ void __launch_bounds__(128, DRT_BWD_MINB) trace_bwd_kernel(BvhView B, const double* __restrict__ V64,
                                                         const double* __restrict__ origin, const double* __restrict__ dir,
                                                         double ext_ior, double int_ior, const int4* __restrict__ rec,
                                                         const int* __restrict__ rec_count,
