@@ -109,6 +109,8 @@ def run_reference(args):
         return
     from drt_b200 import configs
     from oracle import oracle
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and uses all host cores
+    oracle.set_num_threads(len(os.sched_getaffinity(0)))
     cfg = configs.make(args.config)
     nv = max(1, min(args.ref_views, cfg["n_views"]))
     stride = max(1, cfg["n_views"] // nv)
@@ -550,6 +552,7 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
         nvb = max(1, min(args.cpu_views, n_views))
         stride = max(1, n_views // nvb)
         ccams = cfg["cams"][::stride][:nvb]
