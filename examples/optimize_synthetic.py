@@ -38,10 +38,12 @@ def optimize(vertices0, faces, data, hp, iters, log_every=10, fused_loss=True):
         vertices = init_vertices + parameter
         scene.update_verticex(vertices)                                           # optim.py:203
         # ray loss (optim.py:91-108)
-        screen, valid, _, origin, ray_dir, _ = data.get_view(next(ray_view))
+        k = next(ray_view)
         if fused_loss:
-            ray_loss = losses.ray_loss(scene, origin, ray_dir, screen, valid)
+            # the whole of optim.py:93-106 (+ its backward) in one library call, from the loader's compact view
+            ray_loss = losses.ray_loss_view(scene, data.get_view_compact(k))
         else:
+            screen, valid, _, origin, ray_dir, _ = data.get_view(k)
             out_ori, out_dir, mask = scene.render_transparent(origin, ray_dir)
             target = screen - out_ori.detach()
             target = target / target.norm(dim=1, keepdim=True)
