@@ -587,6 +587,7 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": workload_name(cfg, n_views), "rays_per_step": n_total, "views_per_gpu": len(cams),
                        "parallelism": f"views sharded over {world} GPU(s), mesh/BVH replicated, 1 all-reduce of grad_V",
+                       "allreduce": ("none" if world == 1 else "peer-memory one-shot kernel (drt_comm_*)" if ddist.peer_allreduce(1, dev) is not None else "torch.distributed/NCCL"),
                        "bvh": "refit each step" if args.refit else "full LBVH rebuild each step", "loss_path": args.loss_path,
                        "l2": "inputs larger than L2 (%.1f GB of rays per step per GPU)" % (n_local * 48 / 1e9),
                        "int_ior": configs.INT_IOR, "valid_frac_rank0": valid_frac},
@@ -597,6 +598,9 @@ def run_b200(args):
         }
         print(json.dumps(out), flush=True)
     if world > 1:
+        pc = ddist.peer_allreduce(1, dev)
+        if pc is not None and pc.timed_out():
+            raise SystemExit("peer all-reduce: a wait for a peer ran into the spin limit -- results invalid")
         dist.barrier()
         dist.destroy_process_group()
 

@@ -6,6 +6,7 @@
 
 #include "../../include/drt_b200.h"
 #include "loss_step.cuh"
+#include "peer_allreduce.cuh"
 
 using namespace drt;
 
@@ -629,6 +630,117 @@ int drt_generate_rays(int32_t resy, int32_t resx, const double* K_inverse, const
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_for(n, 256), (int64_t)sms * 16));
     generate_rays_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(resy, resx, K_inverse, R_inverse, origin3, dir); ++g_launches;
     CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+// ---- peer-memory all-reduce of grad_V ------------------------------------------------------
+struct drt_comm {
+    int device = 0, rank = 0, world = 1;
+    int64_t stride = 0;             // doubles per parity half of the staging buffer
+    unsigned char* region = nullptr; // local IPC-exported region: [2*stride doubles][2*kMaxPeers flags][arrive][error]
+    void* peer_region[drt::kMaxPeers] = {};
+    bool connected = false;
+    unsigned epoch = 0;
+    int sm_count = 148;
+    size_t flags_off = 0;
+};
+
+namespace {
+size_t comm_bytes(int64_t stride) { return (size_t)stride * 2 * sizeof(double) + (2 * drt::kMaxPeers + 2) * sizeof(unsigned); }
+}
+
+int drt_comm_create(int device, int rank, int world, int64_t max_doubles, drt_comm** out)
+{
+    if (!out) return fail(DRT_ERR_INVALID, "drt_comm_create: out is null");
+    *out = nullptr;
+    if (world < 1 || world > drt::kMaxPeers || rank < 0 || rank >= world) return fail(DRT_ERR_INVALID, "drt_comm_create: rank %d / world %d out of range (max %d ranks)", rank, world, drt::kMaxPeers);
+    if (max_doubles < 1) return fail(DRT_ERR_INVALID, "drt_comm_create: max_doubles < 1");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    drt_comm* c = new drt_comm();
+    c->device = device; c->rank = rank; c->world = world;
+    c->stride = (max_doubles + 31) / 32 * 32;
+    c->flags_off = (size_t)c->stride * 2 * sizeof(double);
+    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaMalloc(&c->region, comm_bytes(c->stride)));
+    CU(cudaMemset(c->region, 0, comm_bytes(c->stride)));
+    CU(cudaDeviceSynchronize());
+    c->peer_region[rank] = c->region;
+    *out = c;
+    return DRT_OK;
+}
+
+int drt_comm_handle(const drt_comm* c, unsigned char handle[64])
+{
+    if (!c || !handle) return fail(DRT_ERR_INVALID, "drt_comm_handle: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    DeviceGuard g(c->device);
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->region));
+    memcpy(handle, &h, 64);
+    return DRT_OK;
+}
+
+int drt_comm_connect(drt_comm* c, const unsigned char* handles)
+{
+    if (!c || !handles) return fail(DRT_ERR_INVALID, "drt_comm_connect: null argument");
+    DeviceGuard g(c->device);
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)r, 64);
+        CU(cudaIpcOpenMemHandle(&c->peer_region[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->connected = true;
+    return DRT_OK;
+}
+
+int drt_comm_allreduce_sum_f64(drt_comm* c, double* data, int64_t n, void* stream)
+{
+    if (!c) return fail(DRT_ERR_INVALID, "drt_comm_allreduce_sum_f64: null handle");
+    if (n < 0 || n > c->stride) return fail(DRT_ERR_INVALID, "drt_comm_allreduce_sum_f64: n = %lld exceeds the %lld doubles the communicator was created for", (long long)n, (long long)c->stride);
+    if (n == 0 || c->world == 1) return DRT_OK;
+    if (!data) return fail(DRT_ERR_INVALID, "drt_comm_allreduce_sum_f64: null buffer");
+    if (!c->connected) return fail(DRT_ERR_STATE, "drt_comm_allreduce_sum_f64: drt_comm_connect has not been called");
+    DeviceGuard g(c->device);
+    PeerView pv;
+    for (int r = 0; r < c->world; ++r) {
+        pv.buf[r] = reinterpret_cast<double*>(c->peer_region[r]);
+        pv.flags[r] = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(c->peer_region[r]) + c->flags_off);
+    }
+    unsigned* local = reinterpret_cast<unsigned*>(c->region + c->flags_off);
+    pv.arrive = local + 2 * kMaxPeers;
+    pv.error = local + 2 * kMaxPeers + 1;
+    pv.stride = c->stride;
+    pv.rank = c->rank;
+    pv.world = c->world;
+    // co-resident by construction: at most one block per SM (the blocks spin on the peers' flags)
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_for(n, 512), std::min(c->sm_count, 64)));
+    peer_allreduce_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(pv, data, n, ++c->epoch); ++g_launches;
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_comm_status(const drt_comm* c, void* stream, int* timed_out)
+{
+    if (!c || !timed_out) return fail(DRT_ERR_INVALID, "drt_comm_status: null argument");
+    DeviceGuard g(c->device);
+    unsigned e = 0;
+    CU(cudaMemcpyAsync(&e, c->region + c->flags_off + (2 * kMaxPeers + 1) * sizeof(unsigned), sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    *timed_out = (int)e;
+    return DRT_OK;
+}
+
+int drt_comm_destroy(drt_comm* c)
+{
+    if (!c) return DRT_OK;
+    DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; ++r)
+        if (r != c->rank && c->peer_region[r]) cudaIpcCloseMemHandle(c->peer_region[r]);
+    if (c->region) cudaFree(c->region);
+    delete c;
     return DRT_OK;
 }
 

@@ -188,6 +188,28 @@ DRT_API int drt_ray_loss_step(const drt_bvh* bvh, const double* V64, const doubl
 DRT_API int drt_generate_rays(int32_t resy, int32_t resx, const double* K_inverse, const double* R_inverse, double* origin3,
                       double* dir, void* stream);
 
+/*
+ * The one collective of the path -- SURVEY.md 8(e): views are sharded over the GPUs of one box, the mesh and
+ * BVH are replicated, grad_V float64[nV,3] is summed once per step (the reference itself is single-GPU,
+ * optix_extend.cpp:10, so there is no reference interface to mirror).  One-shot all-reduce over NVLink /
+ * NVSwitch peer memory in ONE kernel launch: every rank stages its gradient in an IPC-exported buffer,
+ * publishes an epoch flag in every peer's memory, waits for the peers' flags and adds all staging buffers in
+ * rank order (all ranks get the same bits).  One process per GPU:
+ *   drt_comm_create   allocates the local staging region for up to max_doubles values
+ *   drt_comm_handle   -> 64-byte cudaIpcMemHandle_t of the region; exchange them with any host-side all-gather
+ *   drt_comm_connect  handles = world x 64 bytes in rank order; opens the peers' regions
+ *   drt_comm_allreduce_sum_f64   data float64[n] (device), in place, asynchronous on `stream`; every rank must
+ *                     call it the same number of times with the same n
+ *   drt_comm_status   synchronises `stream`; timed_out = 1 if a wait for a peer ever ran into the spin limit
+ */
+typedef struct drt_comm drt_comm;
+DRT_API int drt_comm_create(int device, int rank, int world, int64_t max_doubles, drt_comm** out);
+DRT_API int drt_comm_handle(const drt_comm* comm, unsigned char handle[64]);
+DRT_API int drt_comm_connect(drt_comm* comm, const unsigned char* handles);
+DRT_API int drt_comm_allreduce_sum_f64(drt_comm* comm, double* data, int64_t n, void* stream);
+DRT_API int drt_comm_status(const drt_comm* comm, void* stream, int* timed_out);
+DRT_API int drt_comm_destroy(drt_comm* comm);
+
 /* Text of the last error on this thread ("" if none).  Never NULL. */
 DRT_API const char* drt_last_error(void);
 

@@ -94,3 +94,54 @@ def test_full_size_backward_linearity_and_shard_sum(c4):
     sc.update_verticex(V)
     assert (parts - g1).abs().max().item() < 1e-11 * g1.abs().max().item()
     assert torch.isfinite(g1).all() and (g1.abs().sum(dim=1) > 0).float().mean().item() > 0.5   # most vertices receive gradient
+
+
+def test_full_size_fused_step_equals_dense_route_and_shard_sum(c4):
+    """49.8 M rays through drt_ray_loss_step (one origin row per view, sparse targets, 8x4 pixel tiles): the loss and the
+    vertex gradient are those of the route through render_transparent's dense outputs, the number of valid paths is
+    mask.sum(), and the per-rank shards of the 8-GPU configuration add up to the whole batch."""
+    from drt_b200 import losses
+    sc, o, d = c4["scene"], c4["o"], c4["d"]
+    out_ori, out_dir, mask = (t.detach() for t in c4["out"])
+    cfg = c4["cfg"]
+    n_pix, n_views = cfg["resy"] * cfg["resx"], cfg["n_views"]
+    dev = o.device
+    # measured screen points: the exit rays of this very mesh pushed 100 mm out and displaced, on 90 % of the valid paths
+    k = torch.arange(o.shape[0], device=dev, dtype=torch.float64).unsqueeze(1)
+    valid = mask[:, 0] & ((torch.arange(o.shape[0], device=dev) % 10) != 3)
+    screen = ((out_ori + 100.0 * out_dir + 0.5 * torch.sin(k * torch.tensor([[1e-3, 2e-3, 3e-3]], device=dev, dtype=torch.float64))) * valid[:, None]).contiguous()
+    del k
+    origins = torch.stack([o[j * n_pix] for j in range(n_views)])
+    sparse = losses.SparseTargets.from_dense(screen, valid)
+    assert len(sparse) == int(valid.sum().item())
+
+    def run(fn):
+        V = sc.vertices.detach().clone().requires_grad_(True)
+        sc.update_verticex(V)
+        loss = fn()
+        loss.backward()
+        return loss.item(), V.grad.clone()
+
+    n_paths = torch.zeros(1, dtype=torch.int32, device=dev)
+    l_step, g_step = run(lambda: losses.ray_loss(sc, origins, d, targets=sparse, n_paths=n_paths, image_size=(cfg["resy"], cfg["resx"])))
+    assert int(n_paths.item()) == int(mask[:, 0].sum().item())
+    l_rec, g_rec = run(lambda: losses.ray_loss_rec(sc, o, d, screen, valid))
+    assert l_step > 0 and abs(l_step - l_rec) <= 1e-12 * l_rec
+    scale = g_rec.abs().max().item()
+    assert (g_step - g_rec).abs().max().item() < 1e-11 * scale
+    # the reference's dense layout through the same entry point, scanline batches
+    l_dense, g_dense = run(lambda: losses.ray_loss(sc, o, d, screen=screen, valid=valid))
+    assert abs(l_dense - l_rec) <= 1e-12 * l_rec and (g_dense - g_rec).abs().max().item() < 1e-11 * scale
+    # view k -> rank k mod 8: shard losses and gradients add up (what the all-reduce relies on)
+    l_sum, g_sum = 0.0, torch.zeros_like(g_rec)
+    for r in range(8):
+        mine = list(range(r, n_views, 8))
+        sel = torch.cat([torch.arange(j * n_pix, (j + 1) * n_pix, device=dev) for j in mine])
+        d_r, scr_r, val_r = d[sel].contiguous(), screen[sel].contiguous(), valid[sel].contiguous()
+        tg = losses.SparseTargets.from_dense(scr_r, val_r)
+        lr, gr = run(lambda: losses.ray_loss(sc, origins[mine].contiguous(), d_r, targets=tg, image_size=(cfg["resy"], cfg["resx"])))
+        l_sum += lr
+        g_sum += gr
+        del d_r, scr_r, val_r, tg, sel
+    sc.update_verticex(c4["V"])
+    assert abs(l_sum - l_rec) <= 1e-12 * l_rec and (g_sum - g_rec).abs().max().item() < 1e-11 * scale
