@@ -636,8 +636,8 @@ int drt_generate_rays(int32_t resy, int32_t resx, const double* K_inverse, const
 // ---- peer-memory all-reduce of grad_V ------------------------------------------------------
 struct drt_comm {
     int device = 0, rank = 0, world = 1;
-    int64_t stride = 0;             // doubles per parity half of the staging buffer
-    unsigned char* region = nullptr; // local IPC-exported region: [2*stride doubles][2*kMaxPeers flags][arrive][error]
+    int64_t stride = 0;             // doubles per staging slot
+    unsigned char* region = nullptr; // local IPC-exported region: [2 parities][world slots][stride doubles][2*kMaxPeers flags][arrive][error]
     void* peer_region[drt::kMaxPeers] = {};
     bool connected = false;
     unsigned epoch = 0;
@@ -646,7 +646,7 @@ struct drt_comm {
 };
 
 namespace {
-size_t comm_bytes(int64_t stride) { return (size_t)stride * 2 * sizeof(double) + (2 * drt::kMaxPeers + 2) * sizeof(unsigned); }
+size_t comm_bytes(int64_t stride, int world) { return (size_t)stride * 2 * world * sizeof(double) + (2 * drt::kMaxPeers + 2) * sizeof(unsigned); }
 }
 
 int drt_comm_create(int device, int rank, int world, int64_t max_doubles, drt_comm** out)
@@ -660,10 +660,10 @@ int drt_comm_create(int device, int rank, int world, int64_t max_doubles, drt_co
     drt_comm* c = new drt_comm();
     c->device = device; c->rank = rank; c->world = world;
     c->stride = (max_doubles + 31) / 32 * 32;
-    c->flags_off = (size_t)c->stride * 2 * sizeof(double);
+    c->flags_off = (size_t)c->stride * 2 * world * sizeof(double);
     CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    CU(cudaMalloc(&c->region, comm_bytes(c->stride)));
-    CU(cudaMemset(c->region, 0, comm_bytes(c->stride)));
+    CU(cudaMalloc(&c->region, comm_bytes(c->stride, world)));
+    CU(cudaMemset(c->region, 0, comm_bytes(c->stride, world)));
     CU(cudaDeviceSynchronize());
     c->peer_region[rank] = c->region;
     *out = c;
@@ -705,7 +705,7 @@ int drt_comm_allreduce_sum_f64(drt_comm* c, double* data, int64_t n, void* strea
     DeviceGuard g(c->device);
     PeerView pv;
     for (int r = 0; r < c->world; ++r) {
-        pv.buf[r] = reinterpret_cast<double*>(c->peer_region[r]);
+        pv.stage[r] = reinterpret_cast<double*>(c->peer_region[r]);
         pv.flags[r] = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(c->peer_region[r]) + c->flags_off);
     }
     unsigned* local = reinterpret_cast<unsigned*>(c->region + c->flags_off);

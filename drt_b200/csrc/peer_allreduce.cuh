@@ -2,14 +2,15 @@
 //
 // The one collective of the path: views are sharded over the GPUs of one box, the mesh is
 // replicated, and grad_V float64[V,3] (603 KB at C4) is summed once per step.  For a message this small a ring /
-// tree collective is all latency (NCCL: 0.05 ms at 2 GPUs, 0.12 ms at 8 for 603 KB); here every rank
-//   1 copies its gradient into an IPC-exported staging buffer and publishes an epoch flag in EVERY peer's memory,
+// tree collective is all latency; here, in ONE kernel launch, every rank
+//   1 PUSHES its gradient into slot [rank] of an IPC-exported staging area of EVERY rank (posted NVLink stores),
+//     and the last block to finish publishes an epoch flag in every peer's memory (one system fence per block),
 //   2 waits until all peers' flags for this epoch have landed in its own memory,
-//   3 reads all staging buffers straight over NVLink and adds them in rank order (so every rank gets the same
-//     bits, independent of arrival order),
-// in ONE kernel launch.  Staging buffers and flags are double-buffered by epoch parity: a rank may run ahead by one
-// all-reduce, and it cannot start epoch e+2 (which reuses the buffers of epoch e) before every peer has signalled
-// epoch e+1, i.e. has finished reading epoch e.  The grid is kept small enough to be co-resident (blocks spin).
+//   3 adds the slots of its own staging area in rank order (local reads; every rank gets the same bits,
+//     independent of arrival order).
+// Staging slots and flags are double-buffered by epoch parity: a rank may run ahead by one all-reduce, and it
+// cannot start epoch e+2 (which reuses the slots of epoch e) before every peer has signalled epoch e+1, i.e. has
+// finished reading epoch e.  The grid is kept small enough to be co-resident (blocks spin on the flags).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,11 +21,11 @@ constexpr int kMaxPeers = 16;
 constexpr unsigned kSpinLimit = 1u << 26;  // ~ seconds; a peer that never arrives sets the error flag instead of hanging the GPU
 
 struct PeerView {
-    double* buf[kMaxPeers];      // staging buffers of all ranks (buf[r] + parity * stride)
+    double* stage[kMaxPeers];    // staging areas of all ranks: [2 parities][world slots][stride] doubles
     unsigned* flags[kMaxPeers];  // flag blocks of all ranks: [2][kMaxPeers] epochs, written by the peers
     unsigned* arrive;            // local: blocks of this launch that finished stage 1
     unsigned* error;             // local: set when a wait timed out
-    int64_t stride;              // doubles per parity half
+    int64_t stride;              // doubles per slot
     int rank, world;
 };
 
@@ -39,13 +40,16 @@ __device__ __forceinline__ unsigned ld_sys(const unsigned* p)
 __global__ void __launch_bounds__(512) peer_allreduce_kernel(PeerView pv, double* __restrict__ data, int64_t n, unsigned epoch)
 {
     const int par = epoch & 1u;
-    double* mine = pv.buf[pv.rank] + par * pv.stride;
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-    // 1: stage my contribution, then the LAST block of this launch publishes the epoch to every rank (myself included)
-    for (int64_t i = tid; i < n; i += nth) mine[i] = data[i];
-    __threadfence_system();
+    const int64_t slot = ((int64_t)par * pv.world + pv.rank) * pv.stride;   // my slot in everybody's staging area
+    // 1: push my contribution to every rank (myself included)
+    for (int64_t i = tid; i < n; i += nth) {
+        const double v = data[i];
+        for (int r = 0; r < pv.world; ++r) pv.stage[r][slot + i] = v;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();                      // this block's stores (observed through the barrier) before the count
         if (atomicAdd(pv.arrive, 1u) == gridDim.x - 1) {
             *pv.arrive = 0;
             __threadfence_system();
@@ -58,15 +62,15 @@ __global__ void __launch_bounds__(512) peer_allreduce_kernel(PeerView pv, double
         unsigned spins = 0;
         while (ld_sys(f) != epoch) {
             if (++spins > kSpinLimit) { atomicExch(pv.error, 1u); break; }
-            __nanosleep(64);
+            __nanosleep(32);
         }
     }
     __syncthreads();
-    __threadfence_system();
-    // 3: sum the staging buffers in rank order, reading the peers' memory directly
+    // 3: add the slots of my own staging area in rank order
+    const double* mine = pv.stage[pv.rank] + (int64_t)par * pv.world * pv.stride;
     for (int64_t i = tid; i < n; i += nth) {
         double s = 0.0;
-        for (int r = 0; r < pv.world; ++r) s += __ldcv(pv.buf[r] + par * pv.stride + i);
+        for (int r = 0; r < pv.world; ++r) s += __ldcv(mine + r * pv.stride + i);
         data[i] = s;
     }
 }

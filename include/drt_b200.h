@@ -192,9 +192,9 @@ DRT_API int drt_generate_rays(int32_t resy, int32_t resx, const double* K_invers
  * The one collective of the path -- SURVEY.md 8(e): views are sharded over the GPUs of one box, the mesh and
  * BVH are replicated, grad_V float64[nV,3] is summed once per step (the reference itself is single-GPU,
  * optix_extend.cpp:10, so there is no reference interface to mirror).  One-shot all-reduce over NVLink /
- * NVSwitch peer memory in ONE kernel launch: every rank stages its gradient in an IPC-exported buffer,
- * publishes an epoch flag in every peer's memory, waits for the peers' flags and adds all staging buffers in
- * rank order (all ranks get the same bits).  One process per GPU:
+ * NVSwitch peer memory in ONE kernel launch: every rank pushes its gradient into its slot of an IPC-exported
+ * staging area of every rank, publishes an epoch flag in every peer's memory, waits for the peers' flags and
+ * adds the slots of its own area in rank order (all ranks get the same bits).  One process per GPU:
  *   drt_comm_create   allocates the local staging region for up to max_doubles values
  *   drt_comm_handle   -> 64-byte cudaIpcMemHandle_t of the region; exchange them with any host-side all-gather
  *   drt_comm_connect  handles = world x 64 bytes in rank order; opens the peers' regions
