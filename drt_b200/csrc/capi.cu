@@ -58,6 +58,8 @@ struct Tuning {
     bool one_launch = false;  // DRT_ONE_LAUNCH=1: the cooperative single-launch variant (measured 1.5 % slower: spills)
     bool prefer_l1 = false;  // DRT_PREFER_L1=1 forces cudaSharedmemCarveoutMaxL1: measured 22 % SLOWER (the 1 KB/block reserve then caps residency at 4 blocks/SM)
     int bwd_merge = -1;  // DRT_BWD_MERGE = 0 | 1 forces the run-merged backward scatter off / on (default: by rays per vertex)
+    int tile_w_log2 = 3;  // DRT_TILE_SHAPE = 8x4 (default) | 4x8 | 16x2
+    int r_grid = 8;       // DRT_R_GRID: blocks per SM of the dense refraction kernels' grids
     bool tile = true;  // DRT_TILE=0: keep scanline batches in drt_ray_loss_step even when the image size is known (A/B switch)
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
     int thresh = 32;
@@ -84,6 +86,11 @@ struct Tuning {
             if (c && atoi(c) >= 0 && atoi(c) <= 31) vo = atoi(c);
             pol[q] = make_policy(th, vo);
         }
+        const char* ts = getenv("DRT_TILE_SHAPE");
+        if (ts && !strcmp(ts, "4x8")) tile_w_log2 = 2;
+        if (ts && !strcmp(ts, "16x2")) tile_w_log2 = 4;
+        const char* rg = getenv("DRT_R_GRID");
+        if (rg && atoi(rg) >= 1 && atoi(rg) <= 64) r_grid = atoi(rg);
         const char* tl = getenv("DRT_TILE");
         if (tl && !strcmp(tl, "0")) tile = false;
         const char* ol = getenv("DRT_ONE_LAUNCH");
@@ -165,9 +172,10 @@ struct DeviceGuard {
 // 8 x 4 pixel tiles are possible when the N rays are whole images whose sides the tile divides
 TileMap tile_map(int img_w, int img_h, int64_t N)
 {
-    const bool ok = tuning().tile && img_w > 0 && img_h > 0 && img_w % 8 == 0 && img_h % 4 == 0 && (int64_t)img_w * img_h <= N &&
+    const int lg = tuning().tile_w_log2, tw = 1 << lg, th = 32 >> lg;
+    const bool ok = tuning().tile && img_w > 0 && img_h > 0 && img_w % tw == 0 && img_h % th == 0 && (int64_t)img_w * img_h <= N &&
                     N % ((int64_t)img_w * img_h) == 0;
-    return ok ? TileMap{img_w, img_w * img_h} : TileMap{0, 0};
+    return ok ? TileMap{img_w, img_w * img_h, lg} : TileMap{0, 0, lg};
 }
 
 // clamp + count out-of-range indices so that no later kernel can fault on a bad face list
@@ -573,7 +581,7 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
     int* countS = (int*)(ctl + 4);
     const int* pol = tuning().pol;
     const int minb = tuning().minb;
-    const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
+    const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * tuning().r_grid);
     const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
     const RaySrc rays{origin, dir, (int)rays_per_origin};
     const Park park{b->park, (int64_t)(b->capPk / 6)};

@@ -277,13 +277,14 @@ __device__ __forceinline__ void traverse(const BvhView& B, const QRay& r, double
 // measured -10 % on the C4 forward; the lists of the later stages inherit the order.
 struct TileMap {
     int img_w, img_hw;  // image width and pixels per image
+    int tw_log2;        // log2 of the tile width: 3 = 8 x 4 pixels, 2 = 4 x 8
     __device__ __forceinline__ int ray_of(int item) const
     {
         if (!img_w) return item;
         const int v = item / img_hw, r = item - v * img_hw;
-        const int t = r >> 5, w = r & 31, tpr = img_w >> 3;
+        const int t = r >> 5, w = r & 31, tpr = img_w >> tw_log2;
         const int ty = t / tpr, tx = t - ty * tpr;
-        return v * img_hw + (ty * 4 + (w >> 3)) * img_w + tx * 8 + (w & 7);
+        return v * img_hw + (ty * (32 >> tw_log2) + (w >> tw_log2)) * img_w + (tx << tw_log2) + (w & ((1 << tw_log2) - 1));
     }
 };
 
