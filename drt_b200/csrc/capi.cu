@@ -58,7 +58,7 @@ struct Tuning {
     bool one_launch = false;  // DRT_ONE_LAUNCH=1: the cooperative single-launch variant (measured 1.5 % slower: spills)
     bool prefer_l1 = false;  // DRT_PREFER_L1=1 forces cudaSharedmemCarveoutMaxL1: measured 22 % SLOWER (the 1 KB/block reserve then caps residency at 4 blocks/SM)
     int bwd_merge = -1;  // DRT_BWD_MERGE = 0 | 1 forces the run-merged backward scatter off / on (default: by rays per vertex)
-    int tile_w_log2 = 3;  // DRT_TILE_SHAPE = 8x4 (default) | 4x8 | 16x2
+    int tile_w_log2 = 2;  // DRT_TILE_SHAPE = 4x8 (default) | 8x4 | 16x2
     int r_grid = 8;       // DRT_R_GRID: blocks per SM of the dense refraction kernels' grids
     bool tile = true;  // DRT_TILE=0: keep scanline batches in drt_ray_loss_step even when the image size is known (A/B switch)
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
@@ -87,7 +87,7 @@ struct Tuning {
             pol[q] = make_policy(th, vo);
         }
         const char* ts = getenv("DRT_TILE_SHAPE");
-        if (ts && !strcmp(ts, "4x8")) tile_w_log2 = 2;
+        if (ts && !strcmp(ts, "8x4")) tile_w_log2 = 3;
         if (ts && !strcmp(ts, "16x2")) tile_w_log2 = 4;
         const char* rg = getenv("DRT_R_GRID");
         if (rg && atoi(rg) >= 1 && atoi(rg) <= 64) r_grid = atoi(rg);
@@ -169,13 +169,15 @@ struct DeviceGuard {
     }
 };
 
-// 8 x 4 pixel tiles are possible when the N rays are whole images whose sides the tile divides
+// 32-pixel tiles are possible when the N rays are whole images whose sides a tile shape divides
 TileMap tile_map(int img_w, int img_h, int64_t N)
 {
-    const int lg = tuning().tile_w_log2, tw = 1 << lg, th = 32 >> lg;
-    const bool ok = tuning().tile && img_w > 0 && img_h > 0 && img_w % tw == 0 && img_h % th == 0 && (int64_t)img_w * img_h <= N &&
-                    N % ((int64_t)img_w * img_h) == 0;
-    return ok ? TileMap{img_w, img_w * img_h, lg} : TileMap{0, 0, lg};
+    const bool whole = tuning().tile && img_w > 0 && img_h > 0 && (int64_t)img_w * img_h <= N && N % ((int64_t)img_w * img_h) == 0;
+    // preferred shape first (4 x 8 pixels: C4 forward 6.17 ms, 8 x 4: 6.27, 16 x 2: 6.59, 32 x 1 strips: 7.43), then the other one
+    const int shapes[2] = {tuning().tile_w_log2, tuning().tile_w_log2 == 2 ? 3 : 2};
+    for (int lg : shapes)
+        if (whole && img_w % (1 << lg) == 0 && img_h % (32 >> lg) == 0) return TileMap{img_w, img_w * img_h, lg};
+    return TileMap{0, 0, 3};
 }
 
 // clamp + count out-of-range indices so that no later kernel can fault on a bad face list
@@ -600,7 +602,7 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
         else if (minb == 6) KERNEL<6><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
         else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
     } while (0)
-    // whole images of image_w x image_h pixels, both tileable by 8 x 4: a warp's batch becomes a pixel tile
+    // whole images of image_w x image_h pixels that a 32-pixel tile shape divides: a warp's batch becomes a pixel tile
     LossEntryJob j1{rays, b->listA, countL, tile_map(image_w, image_h, N)};
     DRT_LAUNCH_Q(ls_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
     ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park);

@@ -172,7 +172,7 @@ def ray_loss(scene, origin, ray_dir, screen=None, valid=None, targets=None, n_pa
     `origin`: [N,3], expanded/[1,3] (one origin for all rays) or [r,3] with r | N (ray i starts at row i // (N/r)).
     `n_paths`: optional int32[1] device tensor receiving the number of valid two-bounce paths.
     `image_size` = (resy, resx): optional hint that the rays are whole images in scanline order (captured_data.py:26-31);
-    the entry query then works on 8x4 pixel tiles.  Same results either way."""
+    the entry query then works on 32-pixel tiles (4x8, else 8x4).  Same results either way."""
     if (screen is None) == (targets is None):
         raise ValueError("give either screen (+valid) or targets")
     rows, rpo = origin_rows(origin, ray_dir.shape[0])

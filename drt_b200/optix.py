@@ -83,7 +83,7 @@ class optix_mesh:  # noqa: N801  (name fixed by the reference, optix_extend.cpp:
 
     def set_image_size(self, resy, resx):
         """Render resolution hint (the reference's module globals DiffRender.resy / resx, DiffRender.py:16-17): when a
-        batch of rays is whole resy x resx images the entry query works on 8x4 pixel tiles.  Same results either way."""
+        batch of rays is whole resy x resx images the entry query works on 32-pixel tiles (4x8, else 8x4).  Same results either way."""
         if (resy, resx) != getattr(self, "_image_size", None):
             _lib.call("drt_bvh_set_image_size", self._h, int(resx), int(resy))
             self._image_size = (resy, resx)

@@ -66,7 +66,8 @@ DRT_API int drt_bvh_update_vert(drt_bvh* bvh, const float* V32, const double* V6
  * The reference keeps the render resolution in module globals (DiffRender.py:16-17 `resy`, `resx`, assigned
  * by optim.py:179-180); this is their counterpart on the handle.  It is a HINT: when the N rays of a later
  * drt_trace_fwd call are whole images of image_w x image_h pixels in scanline order (N % (w*h) == 0,
- * w % 8 == 0, h % 4 == 0) the entry query walks 8 x 4 pixel tiles per warp instead of 32 x 1 strips.
+ * w % 4 == 0 and h % 8 == 0, or w % 8 == 0 and h % 4 == 0) the entry query walks 32-pixel tiles per warp
+ * instead of 32 x 1 strips.
  * Results do not depend on it.  (0, 0) clears the hint.  Host call, no device work.
  */
 DRT_API int drt_bvh_set_image_size(drt_bvh* bvh, int32_t image_w, int32_t image_h);
@@ -162,8 +163,8 @@ DRT_API int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, 
  *                   point, strictly ascending, tgt_xyz float64[n_tgt,3]; every other ray is
  *                   `valid = False` (captured_data.py:104: valid = screen_pixel[:,0] != 0)
  *   image_w/h       optional hint (0, 0 = none): the N rays are whole images of image_w x image_h pixels in
- *                   scanline order (captured_data.py:26-31).  The entry query then walks 8 x 4 pixel tiles
- *                   per warp instead of 32 x 1 strips (needs image_w % 8 == 0, image_h % 4 == 0 and
+ *                   scanline order (captured_data.py:26-31).  The entry query then walks 4 x 8 (or 8 x 4) pixel
+ *                   tiles per warp instead of 32 x 1 strips (needs a tile shape that divides the image and
  *                   N % (image_w * image_h) == 0, otherwise the hint is ignored).  Results do not depend on it.
  *   loss_sum        float64[1], ACCUMULATED into (caller zeroes)
  *   grad_V          float64[nV,3], ACCUMULATED into; NULL = loss value only

@@ -97,7 +97,7 @@ def test_full_size_backward_linearity_and_shard_sum(c4):
 
 
 def test_full_size_fused_step_equals_dense_route_and_shard_sum(c4):
-    """49.8 M rays through drt_ray_loss_step (one origin row per view, sparse targets, 8x4 pixel tiles): the loss and the
+    """49.8 M rays through drt_ray_loss_step (one origin row per view, sparse targets, 32-pixel tiles (4x8, else 8x4)): the loss and the
     vertex gradient are those of the route through render_transparent's dense outputs, the number of valid paths is
     mask.sum(), and the per-rank shards of the 8-GPU configuration add up to the whole batch."""
     from drt_b200 import losses

@@ -83,7 +83,7 @@ def test_loss_step_vs_oracle_and_every_input_layout(cuda_device, mesh, res, ks):
         "sparse targets, origin per ray": run(o, targets=sparse),
         "sparse targets, origin per view": run(per_view, targets=sparse),
         "dense targets, origin per view": run(per_view, screen=screen, valid=valid),
-        # image size known: the entry query walks 8x4 pixel tiles instead of 32x1 strips -- same paths, same numbers
+        # image size known: the entry query walks 32-pixel tiles (4x8, else 8x4) instead of 32x1 strips -- same paths, same numbers
         "tiles, sparse targets, origin per view": run(per_view, targets=sparse, image_size=res),
         "tiles, dense targets, origin per ray": run(o, screen=screen, valid=valid, image_size=res),
         "untileable image size hint is ignored": run(per_view, targets=sparse, image_size=(res[0] + 1, res[1])),

@@ -287,7 +287,7 @@ def test_fused_ray_loss_matches_reference_expression(cuda_device):
 
 @pytest.mark.parametrize("res", [(96, 128), (1100, 1200)])
 def test_image_size_hint_changes_nothing_but_the_batching(cuda_device, res):
-    """Render.resy / resx (DiffRender.py:16-17, optim.py:179-180) let the entry query walk 8x4 pixel tiles: outputs,
+    """Render.resy / resx (DiffRender.py:16-17, optim.py:179-180) let the entry query walk 32-pixel tiles (4x8, else 8x4): outputs,
     masks and gradients are those of the scanline batching (small batch: one-launch kernel, large: wavefront)."""
     from drt_b200 import views
     v, f = load_mesh("mouse_vh")
