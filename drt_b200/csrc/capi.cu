@@ -58,7 +58,7 @@ struct Tuning {
     bool one_launch = false;  // DRT_ONE_LAUNCH=1: the cooperative single-launch variant (measured 1.5 % slower: spills)
     bool prefer_l1 = false;  // DRT_PREFER_L1=1 forces cudaSharedmemCarveoutMaxL1: measured 22 % SLOWER (the 1 KB/block reserve then caps residency at 4 blocks/SM)
     int bwd_merge = -1;  // DRT_BWD_MERGE = 0 | 1 forces the run-merged backward scatter off / on (default: by rays per vertex)
-    int tile_w_log2 = 2;  // DRT_TILE_SHAPE = 4x8 (default) | 8x4 | 16x2
+    int tile_w_log2 = 0;  // DRT_TILE_SHAPE = 4x8 | 8x4 | 16x2 forces a shape (default: 4x8 for the fused step, 8x4 with dense outputs)
     int r_grid = 8;       // DRT_R_GRID: blocks per SM of the dense refraction kernels' grids
     bool tile = true;  // DRT_TILE=0: keep scanline batches in drt_ray_loss_step even when the image size is known (A/B switch)
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
@@ -88,6 +88,7 @@ struct Tuning {
         }
         const char* ts = getenv("DRT_TILE_SHAPE");
         if (ts && !strcmp(ts, "8x4")) tile_w_log2 = 3;
+        if (ts && !strcmp(ts, "4x8")) tile_w_log2 = 2;
         if (ts && !strcmp(ts, "16x2")) tile_w_log2 = 4;
         const char* rg = getenv("DRT_R_GRID");
         if (rg && atoi(rg) >= 1 && atoi(rg) <= 64) r_grid = atoi(rg);
@@ -170,11 +171,13 @@ struct DeviceGuard {
 };
 
 // 32-pixel tiles are possible when the N rays are whole images whose sides a tile shape divides
-TileMap tile_map(int img_w, int img_h, int64_t N)
+TileMap tile_map(int img_w, int img_h, int64_t N, bool dense_outputs)
 {
     const bool whole = tuning().tile && img_w > 0 && img_h > 0 && (int64_t)img_w * img_h <= N && N % ((int64_t)img_w * img_h) == 0;
-    // preferred shape first (4 x 8 pixels: C4 forward 6.17 ms, 8 x 4: 6.27, 16 x 2: 6.59, 32 x 1 strips: 7.43), then the other one
-    const int shapes[2] = {tuning().tile_w_log2, tuning().tile_w_log2 == 2 ? 3 : 2};
+    // preferred shape first, then the other one.  Fused step: 4 x 8 pixels (C4 forward 6.17 ms; 8 x 4: 6.27, 16 x 2: 6.59, 32 x 1
+    // strips: 7.43).  Dense outputs: 8 x 4 (6.67 vs 6.90 ms: the rows a warp zero-fills for its misses are 192-byte runs instead of 96)
+    const int first = tuning().tile_w_log2 ? tuning().tile_w_log2 : (dense_outputs ? 3 : 2);
+    const int shapes[2] = {first, first == 2 ? 3 : 2};
     for (int lg : shapes)
         if (whole && img_w % (1 << lg) == 0 && img_h % (32 >> lg) == 0) return TileMap{img_w, img_w * img_h, lg};
     return TileMap{0, 0, 3};
@@ -436,7 +439,7 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
     if (tuning().simple_fwd || (!tuning().force_wavefront && N <= kSimpleMaxRays)) {
         int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
         trace_fwd_kernel<<<grid, 128, 0, st>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir, mask3,
-                                               (int4*)rec, rec_count, hit1, tile_map(b->img_w, b->img_h, N));
+                                               (int4*)rec, rec_count, hit1, tile_map(b->img_w, b->img_h, N, true));
     } else {
         // production path: wavefront of persistent query kernels (wavefront.cuh)
         int rc;
@@ -452,13 +455,13 @@ int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, co
         const bool bulk_ok = tuning().bulk && !(((uintptr_t)out_ori | (uintptr_t)out_dir | (uintptr_t)mask3 | (uintptr_t)hit1) & 15u);
         const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 8);
         EntryJob j1{bulk_ok ? reinterpret_cast<const ZeroTile*>(1) : nullptr, false, origin, dir, out_ori, out_dir, mask3, hit1, b->listA, countL,
-                    tile_map(b->img_w, b->img_h, N)};
+                    tile_map(b->img_w, b->img_h, N, true)};
         const int minb = tuning().minb;
         const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
         if (tuning().one_launch && b->fused_blocks_per_sm > 0) {
             // the whole wavefront as ONE cooperative launch (grid-wide barriers between the stages)
             FwdArgs fa{b->view(), V64, origin, dir, (int)N, ext_ior, int_ior, out_ori, out_dir, mask3, hit1, b->listA, b->listB,
-                       (int4*)rec, rec_count, ctl, {pol[0], pol[1], pol[2]}, bulk_ok ? 1 : 0, tile_map(b->img_w, b->img_h, N)};
+                       (int4*)rec, rec_count, ctl, {pol[0], pol[1], pol[2]}, bulk_ok ? 1 : 0, tile_map(b->img_w, b->img_h, N, true)};
             void* kargs[] = {&fa};
             const bool six = minb == 6 && b->fused6_blocks_per_sm > 0;
             const int per_sm = six ? b->fused6_blocks_per_sm : b->fused_blocks_per_sm;
@@ -603,7 +606,7 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
         else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
     } while (0)
     // whole images of image_w x image_h pixels that a 32-pixel tile shape divides: a warp's batch becomes a pixel tile
-    LossEntryJob j1{rays, b->listA, countL, tile_map(image_w, image_h, N)};
+    LossEntryJob j1{rays, b->listA, countL, tile_map(image_w, image_h, N, false)};
     DRT_LAUNCH_Q(ls_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
     ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park);
     LossExitJob j2{park, b->listA};

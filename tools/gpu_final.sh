@@ -1,7 +1,26 @@
 #!/bin/bash
-# final check of the round: the exact commands the driver runs at round end (GPU tests, smoke, default bench, reference arm)
+# final pass of the round: the driver's own commands (GPU tests, smoke, both bench arms) + the other configs + the ncu passes
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-timeout 300 python bench.py --impl reference > gpurun_out/bench_reference_arm.json 2> gpurun_out/bench_reference_arm.err; cut -c1-200 gpurun_out/bench_reference_arm.json
-timeout 600 python bench.py > gpurun_out/bench_c4_n1.json 2> gpurun_out/bench_c4_n1.err; tail -c 400 gpurun_out/bench_c4_n1.err; cut -c1-400 gpurun_out/bench_c4_n1.json
+timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference_arm.json 2> gpurun_out/bench_reference_arm.err
+timeout 600 python bench.py > gpurun_out/bench_c4_n1.json 2> gpurun_out/bench_c4_n1.err; tail -c 400 gpurun_out/bench_c4_n1.err
+B="python bench.py --no-e2e --no-cpu-baseline --no-ref-chain-gpu"
+timeout 300 $B --config C3 > gpurun_out/bench_c3_n1.json 2> gpurun_out/bench_c3.err
+timeout 300 $B --config C2 > gpurun_out/bench_c2_n1.json 2> gpurun_out/bench_c2.err
+timeout 300 $B --config C5 --views 32 > gpurun_out/bench_c5_32views_n1.json 2> gpurun_out/bench_c5.err
+timeout 300 $B --steps 10 --loss-path rec > gpurun_out/sweep_rec_path.json 2> /dev/null
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv \
+    $B --steps 2 --warmup 3 > gpurun_out/ncu_launch_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"ls_|fit_" -o gpurun_out/prof_step -f \
+    $B --steps 1 --warmup 3 --views 8 > gpurun_out/ncu_full_bench.log 2>&1
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/bench_c*_n1.json") + ["gpurun_out/sweep_rec_path.json"]):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1]); p = d["phases_ms"]
+        e = d.get("e2e") or {}
+        print("%-26s %.3f Grays/s step %.3f ms  build %.3f fwd %.3f bwd %.3f frac %.3f e2e %.3f G" % (f[11:-5], d["value"] / 1e9, d["ms_per_step"], p["bvh_build"], p["fwd"], p["bwd"], d["roofline"]["frac"], e.get("value", 0) / 1e9))
+    except Exception as ex:
+        print(f, "ERR", ex)
+PY
