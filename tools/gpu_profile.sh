@@ -1,5 +1,6 @@
 #!/bin/bash
-# GPU pass 6: final defaults (quantised nodes, defer 3, vote 4, tiles): parity suite, smoke, full bench lines, ncu passes
+# gpurun -- 'bash tools/gpu_profile.sh': parity suite, smoke, the bench lines of every config, A/B of the loss routes, and the two ncu
+# passes (launch list over 2 timed steps; --set full of one 8-view step) whose summaries tools/summarize_profiles.py writes to profiles/
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
