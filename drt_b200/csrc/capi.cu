@@ -139,7 +139,6 @@ struct drt_bvh {
     int* listM = nullptr;      size_t capLM = 0; // loss step: slots of L that survive both refractions
     int* listS = nullptr;      size_t capLS = 0; // loss step: slots of L whose exit ray is unoccluded (the valid paths)
     int* tbucket = nullptr;    size_t capTb = 0; // loss step: bucket table of the sparse screen targets
-    double2* tri64 = nullptr;  size_t capT64 = 0; // loss step: float64 vertices per triangle (80-byte records), regathered every call
     unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
     int work_slot = 0;
     int fused_blocks_per_sm = 0;                 // co-resident blocks of wf_fused_kernel<8> (0: no cooperative launch)
@@ -341,7 +340,7 @@ int drt_bvh_destroy(drt_bvh* b)
     if (!b) return DRT_OK;
     DeviceGuard g(b->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {b->listA, b->listB, b->park, b->listM, b->listS, b->tbucket, b->tri64, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
+    void* ptrs[] = {b->listA, b->listB, b->park, b->listM, b->listS, b->tbucket, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -591,9 +590,6 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
     const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
     const RaySrc rays{origin, dir, (int)rays_per_origin};
     const Park park{b->park, (int64_t)(b->capPk / 6)};
-    if ((rc = ensure(b->tri64, b->capT64, (size_t)(kTri64Doubles / 2) * (size_t)b->nF))) return rc;
-    tri64_kernel<<<blocks_for(b->nF, 256), 256, 0, st>>>(b->F, V64, b->nF, b->tri64); ++g_launches;
-    const TriTable tris{b->tri64};
     const int n_buckets = (int)(N >> kTgtShift) + 2;
     if (target_mode == 1) {
         if ((rc = ensure(b->tbucket, b->capTb, (size_t)n_buckets))) return rc;
@@ -612,10 +608,10 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
     // whole images of image_w x image_h pixels that a 32-pixel tile shape divides: a warp's batch becomes a pixel tile
     LossEntryJob j1{rays, b->listA, countL, tile_map(image_w, image_h, N, false)};
     DRT_LAUNCH_Q(ls_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
-    ls_r1_kernel<<<dgrid, 128, 0, st>>>(tris, rays, ext_ior, int_ior, b->listA, countL, park);
+    ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park);
     LossExitJob j2{park, b->listA};
     DRT_LAUNCH_Q(ls_q2_kernel, b->view(), j2, countL, ctl + 1, pol[1]);
-    ls_r2_kernel<<<dgrid, 128, 0, st>>>(tris, ext_ior, int_ior, b->listA, countL, park, b->listM, countM);
+    ls_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, b->listA, countL, park, b->listM, countM);
     LossOcclusionJob j3{park, b->listM, b->listS, countS};
     DRT_LAUNCH_Q(ls_q3_kernel, b->view(), j3, countM, ctl + 2, pol[2]);
 #undef DRT_LAUNCH_Q
@@ -624,11 +620,11 @@ int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin
     // grid = what is co-resident (the kernel is register-bound at 3-4 blocks per SM): a larger grid-stride grid only adds a ragged last wave
     const int bgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * std::max(1, grad_V ? (merge ? b->bwd_blocks[2] : b->bwd_blocks[1]) : b->bwd_blocks[0]));
     if (!grad_V)
-        ls_loss_bwd_kernel<false, false><<<bgrid, 128, 0, st>>>(b->view(), tris, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, nullptr);
+        ls_loss_bwd_kernel<false, false><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, nullptr);
     else if (merge)
-        ls_loss_bwd_kernel<true, true><<<bgrid, 128, 0, st>>>(b->view(), tris, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
+        ls_loss_bwd_kernel<true, true><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
     else
-        ls_loss_bwd_kernel<true, false><<<bgrid, 128, 0, st>>>(b->view(), tris, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
+        ls_loss_bwd_kernel<true, false><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
     g_launches += 6;
     CU(cudaGetLastError());
     if (n_paths) CU(cudaMemcpyAsync(n_paths, countS, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));

@@ -95,45 +95,6 @@ struct Park {
     }
 };
 
-// Float64 vertices of every triangle, gathered once per step: 80-byte records (a0, a1, a2, pad), 16-byte aligned.
-// R1, R2 and the loss/backward kernel are latency-bound on the chain list entry -> face indices -> three vertex
-// gathers; with the table it is list entry -> one record (five 16-byte loads from one or two lines).
-constexpr int kTri64Doubles = 10;
-
-struct TriTable {
-    const double2* __restrict__ t;
-    __device__ __forceinline__ void load(int id, d3& a0, d3& a1, d3& a2) const
-    {
-        const double2* p = t + (size_t)id * (kTri64Doubles / 2);
-        const double2 w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4];
-        a0 = mk3(w0.x, w0.y, w1.x);
-        a1 = mk3(w1.y, w2.x, w2.y);
-        a2 = mk3(w3.x, w3.y, w4.x);
-    }
-    // the same record again, through a pointer the compiler cannot match with an earlier load: the backward kernel
-    // re-reads hit 1 after hit 2 ON PURPOSE, so that the nine doubles do not stay live (and spill) across hit 2
-    __device__ __forceinline__ void reload(int id, d3& a0, d3& a1, d3& a2) const
-    {
-        const double2* q = t;
-        asm volatile("" : "+l"(q));
-        TriTable{q}.load(id, a0, a1, a2);
-    }
-};
-
-__global__ void __launch_bounds__(256) tri64_kernel(const int32_t* __restrict__ F, const double* __restrict__ V64, int nF,
-                                                    double2* __restrict__ out)
-{
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nF) return;
-    const d3 a0 = ld3(V64 + 3 * (size_t)F[3 * f]), a1 = ld3(V64 + 3 * (size_t)F[3 * f + 1]), a2 = ld3(V64 + 3 * (size_t)F[3 * f + 2]);
-    double2* p = out + (size_t)f * (kTri64Doubles / 2);
-    p[0] = make_double2(a0.x, a0.y);
-    p[1] = make_double2(a0.z, a1.x);
-    p[2] = make_double2(a1.y, a1.z);
-    p[3] = make_double2(a2.x, a2.y);
-    p[4] = make_double2(a2.z, 0.0);
-}
-
 // ---- Q1: entry query over all rays; only hits leave a trace ---------------------------------------
 // Work item -> ray through TileMap (trace.cuh): with the image size known a warp's batch is an 8 x 4 pixel tile
 // (the warp scheduling model, tools/warp_sim, gives -22 % warp-wide steps for Q1 and -10 % for Q2/Q3).
@@ -167,7 +128,7 @@ __global__ void __launch_bounds__(128, MINB) ls_q1_kernel(BvhView B, LossEntryJo
 }
 
 // ---- R1: refraction at the entry hit, dense over L, refracted ray parked at its slot ---------------
-__global__ void __launch_bounds__(128) ls_r1_kernel(TriTable tris, RaySrc rays, double ext_ior,
+__global__ void __launch_bounds__(128) ls_r1_kernel(BvhView B, const double* __restrict__ V64, RaySrc rays, double ext_ior,
                                                     double int_ior, int4* __restrict__ L, const int* __restrict__ countL,
                                                     Park park)
 {
@@ -176,7 +137,7 @@ __global__ void __launch_bounds__(128) ls_r1_kernel(TriTable tris, RaySrc rays, 
         const int4 e = L[k];
         HitRec h;
         d3 a0, a1, a2, o1, d1;
-        tris.load(e.y, a0, a1, a2);
+        load_tri64(B, V64, e.y, a0, a1, a2);
         hit_forward(h, rays.o(e.x), rays.d(e.x), a0, a1, a2, ext_ior, int_ior, o1, d1);
         if (h.tir) L[k].w = 1;  // dead
         else park.store(k, o1, d1);
@@ -207,7 +168,7 @@ __global__ void __launch_bounds__(128, MINB) ls_q2_kernel(BvhView B, LossExitJob
 }
 
 // ---- R2: refraction at the exit hit; exit ray parked in place, surviving SLOTS appended to M ---------
-__global__ void __launch_bounds__(128) ls_r2_kernel(TriTable tris, double ext_ior, double int_ior,
+__global__ void __launch_bounds__(128) ls_r2_kernel(BvhView B, const double* __restrict__ V64, double ext_ior, double int_ior,
                                                     const int4* __restrict__ L, const int* __restrict__ countL, Park park,
                                                     int* __restrict__ M, int* __restrict__ countM)
 {
@@ -219,7 +180,7 @@ __global__ void __launch_bounds__(128) ls_r2_kernel(TriTable tris, double ext_io
             HitRec h;
             d3 a0, a1, a2, o1, d1, o2, d2;
             park.load(k, o1, d1);
-            tris.load(e.z, a0, a1, a2);
+            load_tri64(B, V64, e.z, a0, a1, a2);
             hit_forward(h, o1, d1, a0, a1, a2, ext_ior, int_ior, o2, d2);
             alive = !h.tir;
             if (alive) park.store(k, o2, d2);
@@ -263,7 +224,7 @@ __global__ void __launch_bounds__(128, MINB) ls_q3_kernel(BvhView B, LossOcclusi
 // (optim.py:99-106; out_ori is detached, optim.py:100, so g_out_ori = 0) and runs the analytic reverse
 // of the chain (common.cuh:hit_backward) into grad_V.  GRAD = false: loss value only.
 template <bool GRAD, bool MERGE>
-__global__ void __launch_bounds__(128, DRT_BWD_MINB) ls_loss_bwd_kernel(BvhView B, TriTable tris, RaySrc rays,
+__global__ void __launch_bounds__(128, DRT_BWD_MINB) ls_loss_bwd_kernel(BvhView B, const double* __restrict__ V64, RaySrc rays,
                                                              double ext_ior, double int_ior, const int4* __restrict__ L,
                                                              const int* __restrict__ S, const int* __restrict__ countS,
                                                              TargetSrc tgt, double* __restrict__ loss_sum,
@@ -286,12 +247,12 @@ __global__ void __launch_bounds__(128, DRT_BWD_MINB) ls_loss_bwd_kernel(BvhView 
                 d3 a0, a1, a2, o1, d1, o2, d2, go1, gd1, go0, gd0;
                 {
                     HitRec h;
-                    tris.load(e.y, a0, a1, a2);
+                    load_tri64(B, V64, e.y, a0, a1, a2);
                     hit_forward(h, o, d, a0, a1, a2, ext_ior, int_ior, o1, d1);
                 }
                 {
                     HitRec h;
-                    tris.load(e.z, a0, a1, a2);
+                    load_tri64(B, V64, e.z, a0, a1, a2);
                     hit_forward(h, o1, d1, a0, a1, a2, ext_ior, int_ior, o2, d2);
                     d3 tg = sp - o2;
                     tg = divs(tg, __dsqrt_rn(dot(tg, tg)));
@@ -301,7 +262,7 @@ __global__ void __launch_bounds__(128, DRT_BWD_MINB) ls_loss_bwd_kernel(BvhView 
                 }
                 if (GRAD) {
                     HitRec h;
-                    tris.reload(e.y, a0, a1, a2);
+                    load_tri64(B, V64, e.y, a0, a1, a2);
                     hit_forward(h, o, d, a0, a1, a2, ext_ior, int_ior, o1, d1);
                     hit_backward(h, go1, gd1, g1, go0, gd0);
                     id1 = e.y; id2 = e.z;
