@@ -247,7 +247,7 @@ __global__ void grid_kernel(const float4* __restrict__ blo, const float4* __rest
     float ext[3] = {__fadd_ru(h.x, -l.x), __fadd_ru(h.y, -l.y), __fadd_ru(h.z, -l.z)};
     const float lo[3] = {l.x, l.y, l.z};
     float emax = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
-    if (!(emax > 0.f)) emax = 1.f;  // a single point
+    if (!(emax > 7.888609052210118e-31f)) emax = 1.f;  // a single point (or an extent below 2^-100: 1/s must stay finite)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float e = fmaxf(ext[k], emax * 9.5367431640625e-07f);  // flat axis: keep a positive step (2^-20 of the largest extent)
