@@ -140,7 +140,7 @@ typedef struct {
     double c_node, c_push, c_leaf, c_refill;
 } policy;
 
-typedef struct { double cost, node_iters, node_lane_steps, leaf_iters, leaf_lane_tests, refills; long rays, hits; } stats;
+typedef struct { double cost, node_iters, node_lane_steps, leaf_iters, leaf_lane_tests, refills, node_lines, leaf_lines; long rays, hits; } stats;
 
 static const float* RO; static const float* RD; /* ray arrays */
 
@@ -171,14 +171,21 @@ static void run_warp(int first, int last, const policy* P, stats* S, int* out_id
             /* ---- walk phase ---- */
             for (;;) {
                 int any_node = 0, any_push = 0, blocked = 0, can = 0;
+                int seen[32], nseen = 0;   /* distinct nodes fetched by the warp in this iteration ~ L1 wavefronts per load instruction */
                 for (int l = 0; l < 32; ++l) {
                     lane* L = &W[l];
                     if (L->item < 0 || L->node == DONE || L->nd >= P->defer) continue;
                     ++can;
-                    if (L->node >= 0) { L->node = node_step(L); any_node = 1; S->node_lane_steps += 1; }
+                    if (L->node >= 0) {
+                        int dup = 0;
+                        for (int k = 0; k < nseen; ++k) dup |= seen[k] == L->node;
+                        if (!dup) seen[nseen++] = L->node;
+                        L->node = node_step(L); any_node = 1; S->node_lane_steps += 1;
+                    }
                     else { L->q[L->nd++] = L->node; L->node = L->sp ? L->stack[--L->sp] : DONE; any_push = 1; }
                 }
                 if (!can) break;
+                S->node_lines += nseen;
                 S->cost += any_node * P->c_node + any_push * P->c_push;
                 S->node_iters += any_node;
                 if (P->vote_drain > 0) {
@@ -231,8 +238,9 @@ static void* slurp(const char* path, size_t* bytes)
 
 static void report(const char* name, const stats* S, const stats* base)
 {
-    printf("%-44s cost/ray %8.1f (x%.3f)  node iters/ray %6.2f lanes/iter %5.2f  leaf iters/ray %5.2f lanes/iter %5.2f\n", name,
+    printf("%-44s cost/ray %8.1f (x%.3f)  node iters/ray %6.2f lanes/iter %5.2f nodes/iter %5.2f (per ray %6.2f)  leaf iters/ray %5.2f lanes/iter %5.2f\n", name,
            S->cost / S->rays, base ? S->cost / base->cost : 1.0, S->node_iters / S->rays, S->node_lane_steps / S->node_iters,
+           S->node_lines / S->node_iters, S->node_lines / S->rays,
            S->leaf_iters / S->rays, S->leaf_lane_tests / (S->leaf_iters > 0 ? S->leaf_iters : 1));
 }
 
