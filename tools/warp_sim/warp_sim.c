@@ -255,7 +255,12 @@ int main(int argc, char** argv)
     int any = argc > 3 && !strcmp(argv[3], "any");
     int warps = n / 32 / 8; if (warps < 1) warps = 1; if (warps > 4736) warps = 4736;   /* >= 8 batches per warp */
     printf("%d verts, %d tris, %d nodes, %d rays, %d simulated warps, %s\n", nV, nF, nN, n, warps, any ? "any-hit" : "closest-hit");
-    const double CN = 45, CP = 6, CL = 90, CR = 60;
+    /* cost weights in issue slots: node step, leaf push, leaf test, refill round (override: SIM_CN / SIM_CP / SIM_CL / SIM_CR) */
+    double CN = 45, CP = 6, CL = 90, CR = 60;
+    if (getenv("SIM_CN")) CN = atof(getenv("SIM_CN"));
+    if (getenv("SIM_CP")) CP = atof(getenv("SIM_CP"));
+    if (getenv("SIM_CL")) CL = atof(getenv("SIM_CL"));
+    if (getenv("SIM_CR")) CR = atof(getenv("SIM_CR"));
     policy base = {2, 32, 0, any, CN, CP, CL, CR};
     int* hid = malloc(sizeof(int) * n); double* ht = malloc(sizeof(double) * n);
     stats S0 = run(n, &base, warps, hid, ht);
