@@ -21,6 +21,24 @@ def shard_views(n_views, rank, world):
     return list(range(rank, n_views, world))
 
 
+def shard_views_balanced(costs, rank, world):
+    """Views -> ranks by estimated cost instead of round-robin: longest-processing-time-first (views sorted by cost,
+    each given to the least loaded rank; ties -> lower view / lower rank), deterministic, so every rank computes the same
+    assignment from the same costs.  The all-reduce phase of a step is the ranks' arrival skew; the cost of
+    a view is dominated by the rays that hit the object, so `costs` can be the number of measured pixels per view
+    (len(view.targets)) or last iteration's valid-path counts.  Returns this rank's views in ascending order."""
+    costs = [float(c) for c in costs]
+    order = sorted(range(len(costs)), key=lambda k: (-costs[k], k))
+    load = [0.0] * world
+    mine = []
+    for k in order:
+        r = min(range(world), key=lambda j: (load[j], j))
+        load[r] += costs[k]
+        if r == rank:
+            mine.append(k)
+    return sorted(mine)
+
+
 class PeerAllReduce:
     """In-place SUM all-reduce of float64 CUDA tensors of up to `max_doubles` elements through drt_comm_*.
     Collective constructor: every rank of `group` must create it at the same point."""

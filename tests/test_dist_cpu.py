@@ -66,6 +66,20 @@ def test_view_sharding_and_grad_allreduce_gloo():
     assert rel < 1e-12 and dl < 1e-9 and d2 == 0.0
 
 
+def test_balanced_view_sharding():
+    from drt_b200 import dist as ddist
+    rng = np.random.default_rng(3)
+    costs = (1.0 + 0.5 * np.sin(np.arange(72) / 72 * 4 * np.pi) + 0.1 * rng.random(72)).tolist()   # coverage varies with the azimuth
+    for world in (1, 2, 4, 8):
+        parts = [ddist.shard_views_balanced(costs, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(72))                      # a partition
+        load = [sum(costs[k] for k in p) for p in parts]
+        rr = [sum(costs[k] for k in ddist.shard_views(72, r, world)) for r in range(world)]
+        assert max(load) <= max(rr) + 1e-12                                   # never worse than round-robin here
+        assert max(load) - min(load) <= max(costs)                            # LPT bound
+    assert ddist.shard_views_balanced([1, 1, 1, 1], 1, 2) == [1, 3]           # ties: stable and deterministic
+
+
 def test_allreduce_is_identity_without_process_group():
     from drt_b200 import dist as ddist
     g = torch.ones(4, 3, dtype=torch.float64)
