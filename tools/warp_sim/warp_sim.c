@@ -79,6 +79,35 @@ static void build_bvh(void)
     free(cen);
 }
 
+/* ---- optional 4-wide collapse of the binary tree (SIM_BVH4=1): every node absorbs its internal children ------------ */
+typedef struct { box b[4]; int c[4]; int n; } node4;
+static node4* N4; static int* map4;  /* binary node -> wide node index */
+static int use4 = 0;
+
+static int collapse(int n)
+{
+    int me = map4[n];
+    node4* w = &N4[me];
+    w->n = 0;
+    for (int i = 0; i < 2; ++i) {
+        int c = N[n].c[i];
+        if (c >= 0) {  /* internal child: take ITS two children */
+            for (int j = 0; j < 2; ++j) { w->b[w->n] = N[c].b[j]; w->c[w->n] = N[c].c[j]; ++w->n; }
+        } else { w->b[w->n] = N[n].b[i]; w->c[w->n] = c; ++w->n; }
+    }
+    for (int k = 0; k < w->n; ++k)
+        if (w->c[k] >= 0) { int child = w->c[k]; w->c[k] = map4[child]; collapse(child); }
+    return me;
+}
+
+static void build_bvh4(void)
+{
+    N4 = malloc(sizeof(node4) * (nN > 0 ? nN : 1));
+    map4 = malloc(sizeof(int) * (nN > 0 ? nN : 1));
+    for (int i = 0; i < nN; ++i) map4[i] = i;   /* sparse reuse of binary indices: only visited ones matter */
+    if (nN > 0) collapse(0);
+}
+
 /* ---- per-lane traversal state ---------------------------------------------------------------- */
 #define STACK 128
 #define MAXDEFER 16
@@ -92,8 +121,26 @@ typedef struct {
 } lane;
 #define DONE INT32_MIN
 
+static int node_step4(lane* L)
+{
+    const node4* n = &N4[L->node];
+    float tn[4]; int id[4], m = 0;
+    for (int c = 0; c < n->n; ++c) {
+        float a = 0.f, b = L->tmax;
+        for (int k = 0; k < 3; ++k) {
+            float t0 = (n->b[c].lo[k] - L->o[k]) * L->inv[k], t1 = (n->b[c].hi[k] - L->o[k]) * L->inv[k];
+            a = fmaxf(a, fminf(t0, t1)); b = fminf(b, fmaxf(t0, t1));
+        }
+        if (a <= b * 1.000001f) { int j = m++; while (j > 0 && tn[j - 1] > a) { tn[j] = tn[j - 1]; id[j] = id[j - 1]; --j; } tn[j] = a; id[j] = n->c[c]; }
+    }
+    if (!m) return L->sp ? L->stack[--L->sp] : DONE;
+    for (int j = m - 1; j >= 1; --j) L->stack[L->sp++] = id[j];   /* farthest first, nearest popped first */
+    return id[0];
+}
+
 static int node_step(lane* L)
 {
+    if (use4) return node_step4(L);
     const node* n = &N[L->node];
     float tn[2], tf[2]; int h[2];
     for (int c = 0; c < 2; ++c) {
@@ -250,6 +297,7 @@ int main(int argc, char** argv)
     size_t nb; int* m = slurp(argv[1], &nb);
     nV = m[0]; nF = m[1]; V = (float*)(m + 2); F = (int*)(V + 3 * nV);
     build_bvh();
+    if (getenv("SIM_BVH4")) { use4 = 1; build_bvh4(); }
     int* r = slurp(argv[2], &nb);
     int n = r[0]; RO = (float*)(r + 2); RD = RO + 3 * (size_t)n;
     int any = argc > 3 && !strcmp(argv[3], "any");
