@@ -24,7 +24,7 @@ typedef struct { double a[3], e1[3], e2[3]; int id; } tri;
 
 static int nV, nF, nN;
 static float* V; static int* F;
-static node* N; static tri* T;
+static node* N; static tri* T; static unsigned char* depth_of;  /* depth of every binary node (root = 0) */
 static uint64_t* keys;
 
 static uint32_t spread10(uint32_t v) { v &= 1023; v = (v | v << 16) & 0x30000ff; v = (v | v << 8) & 0x300f00f; v = (v | v << 4) & 0x30c30c3; v = (v | v << 2) & 0x9249249; return v; }
@@ -40,6 +40,7 @@ static void tri_box(int f, box* b)
 static void merge(box* o, const box* a, const box* b) { for (int k = 0; k < 3; ++k) { o->lo[k] = fminf(a->lo[k], b->lo[k]); o->hi[k] = fmaxf(a->hi[k], b->hi[k]); } }
 
 /* recursive split of sorted key range [l, r]; returns link, fills box */
+static int cur_depth = 0;
 static int build(int l, int r, box* out)
 {
     if (l == r) { tri_box((int)(keys[l] & 0xffffffffu), out); return ~l; }
@@ -48,8 +49,11 @@ static int build(int l, int r, box* out)
     int lo = l, hi = r;  /* last index with that bit clear */
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((keys[mid] >> bit) & 1) hi = mid - 1; else lo = mid; }
     int me = nN++;
+    depth_of[me] = (unsigned char)(cur_depth > 255 ? 255 : cur_depth);
     box b0, b1;
+    ++cur_depth;
     int c0 = build(l, lo, &b0), c1 = build(lo + 1, r, &b1);
+    --cur_depth;
     N[me].b[0] = b0; N[me].b[1] = b1; N[me].c[0] = c0; N[me].c[1] = c1;
     merge(out, &b0, &b1);
     return me;
@@ -69,6 +73,7 @@ static void build_bvh(void)
     }
     qsort(keys, nF, sizeof(uint64_t), cmp_u64);
     N = malloc(sizeof(node) * (nF > 1 ? nF - 1 : 1)); nN = 0;
+    depth_of = calloc(nF > 1 ? nF - 1 : 1, 1);
     T = malloc(sizeof(tri) * nF);
     for (int k = 0; k < nF; ++k) {
         int f = (int)(keys[k] & 0xffffffffu);
@@ -83,6 +88,7 @@ static void build_bvh(void)
 typedef struct { box b[4]; int c[4]; int n; } node4;
 static node4* N4; static int* map4;  /* binary node -> wide node index */
 static int use4 = 0;
+static int hot_depth = 10;  /* nodes at depth <= hot_depth (2047 nodes, 64 KB) are taken as L1 hits; SIM_HOT_DEPTH */
 
 static int collapse(int n)
 {
@@ -187,7 +193,7 @@ typedef struct {
     double c_node, c_push, c_leaf, c_refill;
 } policy;
 
-typedef struct { double cost, node_iters, node_lane_steps, leaf_iters, leaf_lane_tests, refills, node_lines, leaf_lines; long rays, hits; } stats;
+typedef struct { double cost, node_iters, node_lane_steps, leaf_iters, leaf_lane_tests, refills, node_lines, leaf_lines, deep_iters; long rays, hits; } stats;
 
 static const float* RO; static const float* RD; /* ray arrays */
 
@@ -219,6 +225,7 @@ static void run_warp(int first, int last, const policy* P, stats* S, int* out_id
             for (;;) {
                 int any_node = 0, any_push = 0, blocked = 0, can = 0;
                 int seen[32], nseen = 0;   /* distinct nodes fetched by the warp in this iteration ~ L1 wavefronts per load instruction */
+                int deep = 0;              /* does any lane fetch a node below the L1-hot top of the tree this iteration? */
                 for (int l = 0; l < 32; ++l) {
                     lane* L = &W[l];
                     if (L->item < 0 || L->node == DONE || L->nd >= P->defer) continue;
@@ -227,12 +234,14 @@ static void run_warp(int first, int last, const policy* P, stats* S, int* out_id
                         int dup = 0;
                         for (int k = 0; k < nseen; ++k) dup |= seen[k] == L->node;
                         if (!dup) seen[nseen++] = L->node;
+                        if (!use4 && depth_of[L->node] > hot_depth) deep = 1;
                         L->node = node_step(L); any_node = 1; S->node_lane_steps += 1;
                     }
                     else { L->q[L->nd++] = L->node; L->node = L->sp ? L->stack[--L->sp] : DONE; any_push = 1; }
                 }
                 if (!can) break;
                 S->node_lines += nseen;
+                S->deep_iters += deep;
                 S->cost += any_node * P->c_node + any_push * P->c_push;
                 S->node_iters += any_node;
                 if (P->vote_drain > 0) {
@@ -285,8 +294,8 @@ static void* slurp(const char* path, size_t* bytes)
 
 static void report(const char* name, const stats* S, const stats* base)
 {
-    printf("%-44s cost/ray %8.1f (x%.3f)  node iters/ray %6.2f lanes/iter %5.2f nodes/iter %5.2f (per ray %6.2f)  leaf iters/ray %5.2f lanes/iter %5.2f\n", name,
-           S->cost / S->rays, base ? S->cost / base->cost : 1.0, S->node_iters / S->rays, S->node_lane_steps / S->node_iters,
+    printf("%-44s cost/ray %8.1f (x%.3f)  node iters/ray %6.2f (deep %4.2f) lanes/iter %5.2f nodes/iter %5.2f (per ray %6.2f)  leaf iters/ray %5.2f lanes/iter %5.2f\n", name,
+           S->cost / S->rays, base ? S->cost / base->cost : 1.0, S->node_iters / S->rays, S->deep_iters / S->rays, S->node_lane_steps / S->node_iters,
            S->node_lines / S->node_iters, S->node_lines / S->rays,
            S->leaf_iters / S->rays, S->leaf_lane_tests / (S->leaf_iters > 0 ? S->leaf_iters : 1));
 }
@@ -298,6 +307,7 @@ int main(int argc, char** argv)
     nV = m[0]; nF = m[1]; V = (float*)(m + 2); F = (int*)(V + 3 * nV);
     build_bvh();
     if (getenv("SIM_BVH4")) { use4 = 1; build_bvh4(); }
+    if (getenv("SIM_HOT_DEPTH")) hot_depth = atoi(getenv("SIM_HOT_DEPTH"));
     int* r = slurp(argv[2], &nb);
     int n = r[0]; RO = (float*)(r + 2); RD = RO + 3 * (size_t)n;
     int any = argc > 3 && !strcmp(argv[3], "any");
