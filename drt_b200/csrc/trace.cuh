@@ -44,6 +44,10 @@ struct RayQ {
 #endif
 };
 
+#ifndef DRT_PREFETCH_PUSHED
+#define DRT_PREFETCH_PUSHED 0
+#endif
+
 #if DRT_QNODE
 // |d| < 2^-80 (including 0) is traced as +-2^-80: finite everywhere below (A 2^23 <= s 2^103), and such a ray moves
 // less than 2^-73 extents along that axis over any distance that matters -- far inside the plane margin.
@@ -111,7 +115,12 @@ __device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float 
     const int c0 = (int)b.z, c1 = (int)b.w;
     if (h0 && h1) {
         const bool first0 = n0 <= n1;
-        stack[sp++] = first0 ? c1 : c0;
+        const int later = first0 ? c1 : c0;
+        stack[sp++] = later;
+#if DRT_PREFETCH_PUSHED
+        // experiment switch (off): pull the postponed child's node towards L1 now, so that popping it later is not an L2 round trip
+        if (later >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(B.nodes + (size_t)later * kNodeQuads));
+#endif
         return first0 ? c0 : c1;
     }
     if (h0) return c0;
