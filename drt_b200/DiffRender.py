@@ -51,6 +51,7 @@ class RefractTrace(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vertices, origin, ray_dir, mesh, int_ior, ext_ior):
         dev = mesh.device
+        optix.check_on(dev, vertices=vertices, origin=origin, ray_dir=ray_dir)
         V = vertices.detach()
         if V.dtype != torch.float64 or origin.dtype != torch.float64 or ray_dir.dtype != torch.float64:
             raise TypeError("render_transparent works in float64 like the reference (DiffRender.py:19)")
@@ -91,6 +92,7 @@ class RefractTrace(torch.autograd.Function):
         g_dir = g_dir.contiguous()
         g_ori = None if g_ori is None else g_ori.contiguous()
         mesh = ctx.mesh
+        optix.check_on(mesh.device, grad_out_dir=g_dir, grad_out_ori=g_ori)
         _lib.call("drt_trace_bwd", mesh._h, _ptr(V), _ptr(o), _ptr(d), n, ctx.iors[0], ctx.iors[1], _ptr(rec),
                   _ptr(rec_count), _ptr(g_ori), _ptr(g_dir), _ptr(grad_V), optix._stream_ptr(mesh.device))
         return grad_V, None, None, None, None, None
@@ -105,6 +107,7 @@ class Scene:
         self.cuda_device = cuda_device
         self.optix_mesh = optix.optix_mesh(cuda_device)
         self.refit = False  # True: update_verticex refits the BVH instead of rebuilding it
+        self._mesh, self._mesh_dirty = None, False
         if mesh_path is not None:
             self.update_mesh(mesh_path)
         elif vertices is not None:
@@ -120,6 +123,21 @@ class Scene:
         assert mesh.is_watertight
         self.set_mesh(mesh.vertices, mesh.faces, mesh)
 
+    @property
+    def mesh(self):
+        """The host-side mesh (`scene.mesh.export(path)`, optim.py:50,226) with CURRENT vertices.  The reference copies
+        the vertices to the host on every update_verticex (DiffRender.py:381); here the D2H copy happens on first
+        access after an update, so an unchanged optim.py exports the optimised mesh and the hot loop pays nothing."""
+        if self._mesh_dirty:
+            self._mesh.vertices = self.vertices.detach().cpu().numpy()
+            self._mesh_dirty = False
+        return self._mesh
+
+    @mesh.setter
+    def mesh(self, m):
+        self._mesh = m
+        self._mesh_dirty = False
+
     def set_mesh(self, vertices, faces, mesh=None):
         self.mesh = mesh if mesh is not None else trimesh_lite.TriMesh(
             vertices.detach().cpu().numpy() if isinstance(vertices, torch.Tensor) else vertices,
@@ -128,6 +146,11 @@ class Scene:
         self.faces = torch.as_tensor(np.asarray(self.mesh.faces), dtype=torch.long).to(self._dev)
         # the float32 cast of DiffRender.py:311 happens inside the library (drt_bvh_build_f64)
         self.optix_mesh.update_mesh(self.faces.to(torch.int32), self.vertices.detach())
+        # a corrupt face list must not render silently (the library clamps bad indices so that no kernel can fault);
+        # checked at load time only -- the read-back synchronises, so it stays off the per-iteration path
+        bad = self.optix_mesh.bad_indices()
+        if bad:
+            raise ValueError(f"{bad} face indices are outside [0, {self.vertices.shape[0]}): corrupt mesh")
         self._edges_ready = False
 
     # DiffRender.py:378-384 (without the per-iteration D2H copy and the dead init_VN)
@@ -141,11 +164,7 @@ class Scene:
         return self.vertices[self.faces]
 
     def sync_mesh(self):
-        """Bring self.mesh.vertices up to date (the reference does this D2H copy every iteration,
-        DiffRender.py:381; here only when the mesh is exported)."""
-        if getattr(self, "_mesh_dirty", False):
-            self.mesh.vertices = self.vertices.detach().cpu().numpy()
-            self._mesh_dirty = False
+        """Kept for callers of the earlier API: `scene.mesh` itself is always current now."""
         return self.mesh
 
     # DiffRender.py:386-392

@@ -2,7 +2,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <memory>
 
 #include "../../include/drt_b200.h"
 #include "loss_step.cuh"
@@ -13,7 +15,7 @@ using namespace drt;
 namespace {
 
 thread_local char g_err[512] = "";
-unsigned long long g_launches = 0;  // kernels of this library launched so far (bench.py's gpu_launches)
+std::atomic<unsigned long long> g_launches{0};  // kernels of this library launched so far (bench.py's gpu_launches)
 
 int fail(int code, const char* fmt, ...)
 {
@@ -170,6 +172,16 @@ struct DeviceGuard {
     }
 };
 
+// device that owns a device pointer (the handle-less entry points launch there, not on the caller's current device)
+cudaError_t device_of(const void* p, int* dev)
+{
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) return e;
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) { *dev = a.device; return cudaSuccess; }
+    return cudaGetDevice(dev);
+}
+
 // 32-pixel tiles are possible when the N rays are whole images whose sides a tile shape divides
 TileMap tile_map(int img_w, int img_h, int64_t N, bool dense_outputs)
 {
@@ -301,7 +313,8 @@ int drt_bvh_create(int device, drt_bvh** out)
     if (device < 0 || device >= count) return fail(DRT_ERR_INVALID, "drt_bvh_create: device %d out of range (%d visible)", device, count);
     DeviceGuard g(device);
     if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-    drt_bvh* b = new drt_bvh();
+    std::unique_ptr<drt_bvh, int (*)(drt_bvh*)> guard(new drt_bvh(), drt_bvh_destroy);  // freed on every early return
+    drt_bvh* b = guard.get();
     b->device = device;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -331,7 +344,7 @@ int drt_bvh_create(int device, drt_bvh** out)
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[0], ls_loss_bwd_kernel<false, false>, 128, 0));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[1], ls_loss_bwd_kernel<true, false>, 128, 0));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[2], ls_loss_bwd_kernel<true, true>, 128, 0));
-    *out = b;
+    *out = guard.release();
     return DRT_OK;
 }
 
@@ -419,11 +432,10 @@ int drt_closest_hit(const drt_bvh* b, const float* ray6, int64_t N, float* T, in
     return DRT_OK;
 }
 
-int drt_trace_fwd(const drt_bvh* b_, const double* V64, const double* origin, const double* dir, int64_t N, double ext_ior,
+int drt_trace_fwd(drt_bvh* b, const double* V64, const double* origin, const double* dir, int64_t N, double ext_ior,
                   double int_ior, double* out_ori, double* out_dir, uint8_t* mask3, int32_t* rec, int32_t* rec_count,
                   uint8_t* hit1, void* stream)
 {
-    drt_bvh* b = const_cast<drt_bvh*>(b_);
     if (!b) return fail(DRT_ERR_INVALID, "drt_trace_fwd: null handle");
     if (!b->built) return fail(DRT_ERR_STATE, "drt_trace_fwd: no mesh has been set (update_mesh first)");
     if (N < 0 || N > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_trace_fwd: N must be in [0, 2^31)");
@@ -526,7 +538,9 @@ int drt_ray_loss_grad(const double* out_ori, const double* out_dir, const uint8_
     if (N == 0) return DRT_OK;
     if (!out_ori || !out_dir || !mask3 || !screen || !g_out_dir) return fail(DRT_ERR_INVALID, "drt_ray_loss_grad: null buffer");
     int dev = 0, sms = 148;
-    CU(cudaGetDevice(&dev));
+    CU(device_of(out_ori, &dev));  // launch on the device that owns the buffers, whatever the caller's current device is
+    DeviceGuard g(dev);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int grid = (int)std::min<int64_t>(blocks_for(N, 256), (int64_t)sms * 16);
     ray_loss_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_ori, out_dir, mask3, screen, valid, N, g_out_dir, loss_sum); ++g_launches;
@@ -541,7 +555,9 @@ int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, const do
     if (N == 0) return DRT_OK;
     if (!out_ori || !out_dir || !screen || !rec || !rec_count || !g_out_dir) return fail(DRT_ERR_INVALID, "drt_ray_loss_grad_rec: null buffer");
     int dev = 0, sms = 148;
-    CU(cudaGetDevice(&dev));
+    CU(device_of(out_ori, &dev));
+    DeviceGuard g(dev);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int grid = (int)std::min<int64_t>(blocks_for(N, 256), (int64_t)sms * 8);
     ray_loss_rec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out_ori, out_dir, screen, valid, (const int4*)rec, rec_count, g_out_dir, loss_sum);
@@ -550,12 +566,11 @@ int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, const do
     return DRT_OK;
 }
 
-int drt_ray_loss_step(const drt_bvh* b_, const double* V64, const double* origin, int64_t rays_per_origin, const double* dir,
+int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64_t rays_per_origin, const double* dir,
                       int64_t N, double ext_ior, double int_ior, int target_mode, const double* screen, const uint8_t* valid,
                       const int32_t* tgt_idx, const double* tgt_xyz, int64_t n_tgt, int32_t image_w, int32_t image_h,
                       double* loss_sum, double* grad_V, int32_t* n_paths, void* ev_after_fwd, void* stream)
 {
-    drt_bvh* b = const_cast<drt_bvh*>(b_);
     if (!b) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: null handle");
     if (!b->built) return fail(DRT_ERR_STATE, "drt_ray_loss_step: no mesh has been set (update_mesh first)");
     if (N < 0 || N > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: N must be in [0, 2^31)");
@@ -637,7 +652,9 @@ int drt_generate_rays(int32_t resy, int32_t resx, const double* K_inverse, const
     if (resy < 0 || resx < 0 || (int64_t)resy * resx > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_generate_rays: bad resolution %d x %d", resy, resx);
     if (!K_inverse || !R_inverse || !origin3 || (!dir && (int64_t)resy * resx > 0)) return fail(DRT_ERR_INVALID, "drt_generate_rays: null buffer");
     int dev = 0, sms = 148;
-    CU(cudaGetDevice(&dev));
+    CU(device_of(origin3, &dev));
+    DeviceGuard g(dev);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t n = (int64_t)resy * resx;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_for(n, 256), (int64_t)sms * 16));
@@ -656,6 +673,7 @@ struct drt_comm {
     unsigned epoch = 0;
     int sm_count = 148;
     size_t flags_off = 0;
+    unsigned long long timeout_ns = 120ull * 1000000000ull;  // DRT_PEER_TIMEOUT_S
 };
 
 namespace {
@@ -670,8 +688,11 @@ int drt_comm_create(int device, int rank, int world, int64_t max_doubles, drt_co
     if (max_doubles < 1) return fail(DRT_ERR_INVALID, "drt_comm_create: max_doubles < 1");
     DeviceGuard g(device);
     if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-    drt_comm* c = new drt_comm();
+    std::unique_ptr<drt_comm, int (*)(drt_comm*)> guard(new drt_comm(), drt_comm_destroy);  // freed on every early return
+    drt_comm* c = guard.get();
     c->device = device; c->rank = rank; c->world = world;
+    if (const char* to = getenv("DRT_PEER_TIMEOUT_S"))
+        if (atof(to) > 0) c->timeout_ns = (unsigned long long)(atof(to) * 1e9);
     c->stride = (max_doubles + 31) / 32 * 32;
     c->flags_off = (size_t)c->stride * 2 * world * sizeof(double);
     CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -679,7 +700,7 @@ int drt_comm_create(int device, int rank, int world, int64_t max_doubles, drt_co
     CU(cudaMemset(c->region, 0, comm_bytes(c->stride, world)));
     CU(cudaDeviceSynchronize());
     c->peer_region[rank] = c->region;
-    *out = c;
+    *out = guard.release();
     return DRT_OK;
 }
 
@@ -725,6 +746,7 @@ int drt_comm_allreduce_sum_f64(drt_comm* c, double* data, int64_t n, void* strea
     pv.arrive = local + 2 * kMaxPeers;
     pv.error = local + 2 * kMaxPeers + 1;
     pv.stride = c->stride;
+    pv.timeout_ns = c->timeout_ns;
     pv.rank = c->rank;
     pv.world = c->world;
     // co-resident by construction: at most one block per SM (the blocks spin on the peers' flags)

@@ -18,7 +18,10 @@
 namespace drt {
 
 constexpr int kMaxPeers = 16;
-constexpr unsigned kSpinLimit = 1u << 26;  // ~ seconds; a peer that never arrives sets the error flag instead of hanging the GPU
+// A peer that never arrives must not hang the GPU, and it must not be summed either: the wait is bounded in WALL-CLOCK
+// time (%globaltimer, nanoseconds; PeerView::timeout_ns, default 120 s, DRT_PEER_TIMEOUT_S) and expiry is FATAL -- the
+// error word is set and the kernel traps, so the stale staging slots are never added into grad_V and every later
+// CUDA call of the process fails loudly (drt_comm_status reports it when the context is still alive).
 
 struct PeerView {
     double* stage[kMaxPeers];    // staging areas of all ranks: [2 parities][world slots][stride] doubles
@@ -26,8 +29,16 @@ struct PeerView {
     unsigned* arrive;            // local: blocks of this launch that finished stage 1
     unsigned* error;             // local: set when a wait timed out
     int64_t stride;              // doubles per slot
+    unsigned long long timeout_ns;  // wall-clock bound of the wait for the peers
     int rank, world;
 };
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned ld_sys(const unsigned* p)
@@ -59,9 +70,14 @@ __global__ void __launch_bounds__(512) peer_allreduce_kernel(PeerView pv, double
     // 2: wait for every rank's flag of this epoch in MY memory
     if ((int)threadIdx.x < pv.world) {
         const unsigned* f = pv.flags[pv.rank] + par * kMaxPeers + threadIdx.x;
+        const unsigned long long t0 = global_ns();
         unsigned spins = 0;
         while (ld_sys(f) != epoch) {
-            if (++spins > kSpinLimit) { atomicExch(pv.error, 1u); break; }
+            if ((++spins & 1023u) == 0 && global_ns() - t0 > pv.timeout_ns) {
+                atomicExch(pv.error, 1u);
+                __threadfence_system();
+                __trap();  // fatal: never fall through to the sum with a peer's slot missing
+            }
             __nanosleep(32);
         }
     }

@@ -11,6 +11,7 @@
 // A tile is 256 threads x 8 keys; stability needs the (warp, round, lane) order to equal the key order,
 // hence the warp-blocked item assignment below.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -115,7 +116,7 @@ inline int sort_tiles(int n) { return (n + kSortTile - 1) / kSortTile; }
 
 // Sorts n keys on bits [first_bit, 64); buf holds 2n keys (keys in the first half on entry), table holds
 // 256 * sort_tiles(n) counters.  Returns the half that holds the sorted keys.  5 passes x 2 launches.
-inline uint64_t* sort_keys_u64(uint64_t* buf, int n, int first_bit, unsigned* table, cudaStream_t st, unsigned long long* launches)
+inline uint64_t* sort_keys_u64(uint64_t* buf, int n, int first_bit, unsigned* table, cudaStream_t st, std::atomic<unsigned long long>* launches)
 {
     uint64_t* a = buf;
     uint64_t* b = buf + n;

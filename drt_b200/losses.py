@@ -24,6 +24,7 @@ class RayLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vertices, origin, ray_dir, screen, valid, mesh, int_ior, ext_ior):
         dev = mesh.device
+        optix.check_on(dev, vertices=vertices, origin=origin, ray_dir=ray_dir, screen=screen, valid=valid)
         V = vertices.detach().contiguous()
         o, d = origin.detach().contiguous(), ray_dir.detach().contiguous()
         scr = screen.detach().contiguous()
@@ -123,6 +124,8 @@ class RayLossStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vertices, origin, rpo, ray_dir, screen, valid, targets, mesh, int_ior, ext_ior, n_paths, ev_after_fwd, image_size):
         dev = mesh.device
+        optix.check_on(dev, vertices=vertices, origin=origin, ray_dir=ray_dir, screen=screen, valid=valid, n_paths=n_paths,
+                       **({"targets.idx": targets.idx, "targets.xyz": targets.xyz} if targets is not None else {}))
         V = vertices.detach().contiguous()
         o, d = origin.detach(), ray_dir.detach().contiguous()
         if not (V.dtype == o.dtype == d.dtype == torch.float64):

@@ -19,6 +19,19 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def check_on(device, **tensors):
+    """Every tensor handed to a kernel by raw pointer must live on the handle's CUDA device: a CPU tensor or one on
+    another GPU would be an illegal address inside the kernel (a sticky context error), not a Python exception."""
+    device = torch.device(device)
+    for name, t in tensors.items():
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+        if t.device != device:
+            raise ValueError(f"{name} is on {t.device}, the mesh lives on {device}")
+
+
 class optix_mesh:  # noqa: N801  (name fixed by the reference, optix_extend.cpp:6)
     """Ray-query object over one triangle mesh on one CUDA device."""
 

@@ -33,6 +33,12 @@ extern "C" {
 #define DRT_ERR_CUDA 2    /* a CUDA runtime call failed; see drt_last_error() */
 #define DRT_ERR_STATE 3   /* query before any build (reference: assert(builded), optix_extend.cpp:30) */
 
+/*
+ * A handle is SINGLE-STREAM and SINGLE-THREAD, like the reference object it replaces (one optix_mesh, called from the
+ * Python main thread, query->execute(0) blocking: optix_extend.cpp:45): drt_trace_fwd, drt_ray_loss_step and
+ * drt_silhouette_* use wavefront lists, parked rays and work counters that live IN the handle, so two calls on the same
+ * handle must be ordered on one stream (or by events).  Use one handle per stream for concurrent queries.
+ */
 typedef struct drt_bvh drt_bvh;
 
 /* Replaces optix_mesh::optix_mesh(unsigned cuda_device) -- optix_extend.cpp:8-12. */
@@ -110,7 +116,7 @@ DRT_API int drt_closest_hit(const drt_bvh* bvh, const float* ray6, int64_t N, fl
  *   hit1           optional uint8[N]: 1 where the primary ray hits anything = Scene.render_mask
  *                  (DiffRender.py:434-438) as a by-product.  May be NULL.
  */
-DRT_API int drt_trace_fwd(const drt_bvh* bvh, const double* V64, const double* origin, const double* dir, int64_t N,
+DRT_API int drt_trace_fwd(drt_bvh* bvh, const double* V64, const double* origin, const double* dir, int64_t N,
                   double ext_ior, double int_ior, double* out_ori, double* out_dir, uint8_t* mask3,
                   int32_t* rec, int32_t* rec_count, uint8_t* hit1, void* stream);
 
@@ -174,7 +180,7 @@ DRT_API int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, 
  *                   loss/backward kernel (phase timing for bench.py); NULL = none
  * Scratch (72 B per ray of capacity) lives in the handle and is reused by later calls.
  */
-DRT_API int drt_ray_loss_step(const drt_bvh* bvh, const double* V64, const double* origin, int64_t rays_per_origin,
+DRT_API int drt_ray_loss_step(drt_bvh* bvh, const double* V64, const double* origin, int64_t rays_per_origin,
                       const double* dir, int64_t N, double ext_ior, double int_ior, int target_mode, const double* screen,
                       const uint8_t* valid, const int32_t* tgt_idx, const double* tgt_xyz, int64_t n_tgt, int32_t image_w,
                       int32_t image_h, double* loss_sum, double* grad_V, int32_t* n_paths, void* ev_after_fwd, void* stream);
