@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--loss-path", default="step", choices=["step", "rec", "dense"],
                     help="step: drt_ray_loss_step (default); rec: three-call route; dense: render_transparent + dense loss")
     ap.add_argument("--unfused-loss", action="store_true", help="same as --loss-path dense")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle check of one view of the timed workload")
+    ap.add_argument("--shard", default="balanced", choices=["balanced", "roundrobin"],
+                    help="views -> ranks: by estimated cost (measured pixels per view, LPT) or k mod N")
     return ap.parse_args()
 
 
@@ -184,6 +187,60 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------
+# parity of the timed workload: one whole view of it against the CPU oracle (outside the timed region)
+# ---------------------------------------------------------------------------------------------
+def parity_check(scene, cfg, V, origin_row, d_view, targets_view, image_size, int_ior):
+    """The fused step on ONE view of the benchmark's own inputs (same rays, same sparse targets, same vertices) against
+    oracle/drt_oracle.c: entry-hit ids of every primary ray, number of valid paths, loss (optim.py:96-106) and vertex
+    gradient (optim.py:210).  -> dict; raises SystemExit when the GPU path and the oracle disagree."""
+    import numpy as np
+    import torch
+    from drt_b200 import losses
+    from oracle import oracle
+    oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    dev = d_view.device
+    n = d_view.shape[0]
+    Vp = V.detach().clone().requires_grad_(True)
+    scene.update_verticex(Vp)
+    n_paths = torch.zeros(1, dtype=torch.int32, device=dev)
+    loss = losses.ray_loss(scene, origin_row, d_view, targets=targets_view, n_paths=n_paths, image_size=image_size)
+    loss.backward()
+    o_full = origin_row.expand(n, 3)
+    _, ID = scene.optix_mesh.intersect(torch.cat([o_full.float(), d_view.float()], dim=1))
+    ids = ID.cpu().numpy()
+    o_np, d_np = o_full.cpu().numpy().copy(), d_view.cpu().numpy()
+    m = oracle.OracleMesh(V.detach().cpu().numpy(), cfg["faces"])
+    q = m.trace_fwd(o_np, d_np, int_ior)
+    screen = np.zeros((n, 3))
+    valid = np.zeros(n, dtype=bool)
+    ti = targets_view.idx.cpu().numpy()
+    screen[ti] = targets_view.xyz.cpu().numpy()
+    valid[ti] = True
+    use = q["mask"][:, 0] & valid
+    tg = screen - q["out_ori"]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        tg = tg / np.linalg.norm(tg, axis=1, keepdims=True)
+    diff = np.where(use[:, None], q["out_dir"] - tg, 0.0)
+    ref_loss = float((diff[use] ** 2).sum())
+    ref_g = m.trace_bwd(o_np, d_np, q["tri1"], q["tri2"], None, 2.0 * diff, int_ior)
+    g = Vp.grad.cpu().numpy()
+    nr = np.linalg.norm(ref_g, axis=1)
+    sel = nr > 1e-9 * nr.max()
+    grad_rel = float((np.linalg.norm(g - ref_g, axis=1)[sel] / nr[sel]).max()) if sel.any() else 0.0
+    grad_glob = float(np.abs(g - ref_g).max() / max(np.abs(ref_g).max(), 1e-300))
+    hit = q["stage"] >= 1
+    ids_equal = bool(np.array_equal(ids >= 0, hit) and np.array_equal(ids[hit], q["tri1"][hit]))
+    loss_rel = abs(loss.item() - ref_loss) / max(abs(ref_loss), 1e-300)
+    out = {"views": 1, "rays": int(n), "oracle": "oracle/drt_oracle.c (canonical LBVH, float64 chain)", "ids_equal": ids_equal,
+           "entry_hits": int(hit.sum()), "valid_paths_gpu": int(n_paths.item()), "valid_paths_oracle": int(q["mask"][:, 0].sum()),
+           "loss_gpu": loss.item(), "loss_oracle": ref_loss, "loss_rel": loss_rel, "grad_rel": grad_rel, "grad_rel_global": grad_glob}
+    out["ok"] = bool(ids_equal and out["valid_paths_gpu"] == out["valid_paths_oracle"] and loss_rel <= 1e-10 and grad_rel <= 1e-7)
+    if not out["ok"]:
+        raise SystemExit("bench.py: the GPU path disagrees with the oracle on the timed workload: " + json.dumps(out))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -215,14 +272,31 @@ def run_b200(args):
         cfg["n_views"] = len(cfg["cams"])
     n_views, resy, resx = cfg["n_views"], cfg["resy"], cfg["resx"]
     n_pix = resy * resx
-    mine = ddist.shard_views(n_views, rank, world)
-    cams = [cfg["cams"][k] for k in mine]
-    n_local = len(cams) * n_pix
     n_total = n_views * n_pix
 
     R.intIOR = configs.INT_IOR
     R.resy, R.resx = resy, resx      # optim.py:179-180 (render_transparent passes it on as the tile hint)
     scene = R.Scene(vertices=cfg["vertices"], faces=cfg["faces"], cuda_device=local)
+    # views -> ranks.  A view's cost is dominated by the rays that hit the object, so ranks that get the wide side views
+    # of a turntable arrive late at the all-reduce; `balanced` = longest-processing-time-first on an estimate every rank
+    # computes identically (entry hits of every 16th pixel row/column through the library's own closest hit).
+    shard_skew = None
+    if world > 1 and args.shard == "balanced":
+        costs = []
+        for cam in cfg["cams"]:
+            o_s, d_s = views.generate_ray(resy, resx, cam[3], cam[2], device=dev)
+            pick = torch.arange(0, n_pix, 61, device=dev)
+            _, ids = scene.optix_mesh.intersect(torch.cat([o_s[pick].float(), d_s[pick].float()], dim=1))
+            costs.append(float((ids >= 0).sum().item()) * 61 + 0.03 * n_pix)
+        del o_s, d_s
+        mine = ddist.shard_views_balanced(costs, rank, world)
+        loads = [sum(costs[k] for k in ddist.shard_views_balanced(costs, r, world)) for r in range(world)]
+        rr = [sum(costs[k] for k in ddist.shard_views(n_views, r, world)) for r in range(world)]
+        shard_skew = {"balanced_max_over_mean": max(loads) / (sum(loads) / world), "roundrobin_max_over_mean": max(rr) / (sum(rr) / world)}
+    else:
+        mine = ddist.shard_views(n_views, rank, world)
+    cams = [cfg["cams"][k] for k in mine]
+    n_local = len(cams) * n_pix
     scene.refit = bool(args.refit)
     V = scene.vertices.clone().requires_grad_(True)
     nV = V.shape[0]
@@ -331,6 +405,33 @@ def run_b200(args):
     value = n_total / (ms_per_step * 1e-3)
     loss_val = float(loss_buf.item())
     grad_norm = float(V.grad.norm().item())
+
+    # ---- parity of the timed workload (rank 0, outside the timed region) and of the collective ----------------
+    parity = ar_check = None
+    if rank == 0 and cams and not args.no_parity_check and args.loss_path == "step":
+        tv_sel = sparse.idx < n_pix
+        parity = parity_check(scene, cfg, V, origins[:1], ray_dir[:n_pix], losses.SparseTargets(sparse.idx[tv_sel], sparse.xyz[tv_sel]),
+                              (resy, resx), configs.INT_IOR)
+        parity["view"] = int(mine[0])
+        scene.update_verticex(V)
+    if world > 1:
+        # the collective the timed steps used (peer-memory kernel or NCCL) against torch.distributed's all_reduce of a copy
+        g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+        x = torch.randn((nV, 3), generator=g, dtype=torch.float64).to(dev) * (1.0 + rank)
+        a, b = x.clone(), x.clone()
+        ddist.allreduce_grad(a)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        rel = ((a - b).abs().max() / b.abs().max()).reshape(1)
+        csum = a.view(torch.int64).sum().reshape(1)     # bit pattern checksum: every rank must hold the same bits
+        cmin, cmax = csum.clone(), csum.clone()
+        dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
+        ar_check = {"vs": "torch.distributed.all_reduce (NCCL) of a copy", "doubles": int(x.numel()), "max_rel_diff": float(rel.item()),
+                    "ranks_bit_identical": bool(cmin.item() == cmax.item()), "ok": bool(rel.item() <= 1e-12 and cmin.item() == cmax.item())}
+        if not ar_check["ok"]:
+            raise SystemExit("bench.py: all-reduce self-check failed: " + json.dumps(ar_check))
+    sync_all()
 
     # ---- e2e: host buffers, copies inside the timed region ----------------------------------
     e2e = e2e_ref_layout = e2e_pinhole = None
@@ -595,6 +696,7 @@ def run_b200(args):
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "e2e": e2e, "e2e_reference_layout": e2e_ref_layout, "e2e_pinhole": e2e_pinhole, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "loss": loss_val, "grad_norm": grad_norm,
+            "parity_check": parity, "allreduce_check": ar_check, "shard": {"policy": args.shard if world > 1 else "none", "skew": shard_skew},
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -91,3 +91,24 @@ def view_batch(cams, resy, resx, device="cpu", out_origin=None, out_dir=None):
         out_origin[k * n:(k + 1) * n] = o
         out_dir[k * n:(k + 1) * n] = d
     return out_origin, out_dir
+
+
+def stratified_sample(cfg, target=65536, device="cpu"):
+    """Every `stride`-th ray of the config's whole ray set (all views, global scanline order), stride = total // target:
+    the sample the roofline denominator is frozen on (profiles/canonical_counters.json) and the headline
+    configs are parity-checked on.  -> (origin [n,3], ray_dir [n,3], stride) float64 numpy.  `device`: where the
+    per-view rays are generated before the sample is picked (a CUDA matmul may round the last ulp differently)."""
+    n_pix = cfg["resy"] * cfg["resx"]
+    total = n_pix * cfg["n_views"]
+    stride = max(1, total // target)
+    os_, ds_ = [], []
+    for k, (_, _, R_inv, K_inv) in enumerate(cfg["cams"]):
+        first = (-(k * n_pix)) % stride  # global index k*n_pix + j must be a multiple of stride
+        idx = np.arange(first, n_pix, stride)
+        if len(idx) == 0:
+            continue
+        o, d = generate_ray(cfg["resy"], cfg["resx"], K_inv, R_inv, device=device)
+        pick = torch.as_tensor(idx, device=device)
+        os_.append(o[pick].cpu().numpy())
+        ds_.append(d[pick].cpu().numpy())
+    return np.concatenate(os_), np.concatenate(ds_), stride

@@ -11,19 +11,7 @@ from oracle import oracle
 OUT = os.path.join(ROOT, "profiles", "canonical_counters.json")
 
 
-def sample_rays(cfg, target=65536):
-    n_pix = cfg["resy"] * cfg["resx"]
-    total = n_pix * cfg["n_views"]
-    stride = max(1, total // target)
-    os_, ds_ = [], []
-    for k, (_, _, R_inv, K_inv) in enumerate(cfg["cams"]):
-        first = (-(k * n_pix)) % stride  # global index k*n_pix + j must be a multiple of stride
-        idx = np.arange(first, n_pix, stride)
-        if len(idx) == 0:
-            continue
-        o, d = views.generate_ray(cfg["resy"], cfg["resx"], K_inv, R_inv)
-        os_.append(o.numpy()[idx]); ds_.append(d.numpy()[idx])
-    return np.concatenate(os_), np.concatenate(ds_), stride
+sample_rays = views.stratified_sample  # shared with tests/test_gpu_headline_parity.py
 
 
 def main():
