@@ -206,7 +206,8 @@ def parity_check(scene, cfg, V, origin_row, d_view, targets_view, image_size, in
     loss = losses.ray_loss(scene, origin_row, d_view, targets=targets_view, n_paths=n_paths, image_size=image_size)
     loss.backward()
     o_full = origin_row.expand(n, 3)
-    _, ID = scene.optix_mesh.intersect(torch.cat([o_full.float(), d_view.float()], dim=1))
+    ray6 = torch.cat([o_full.float(), d_view.float()], dim=1)
+    _, ID = scene.optix_mesh.intersect(ray6)
     ids = ID.cpu().numpy()
     o_np, d_np = o_full.cpu().numpy().copy(), d_view.cpu().numpy()
     m = oracle.OracleMesh(V.detach().cpu().numpy(), cfg["faces"])
@@ -229,7 +230,9 @@ def parity_check(scene, cfg, V, origin_row, d_view, targets_view, image_size, in
     grad_rel = float((np.linalg.norm(g - ref_g, axis=1)[sel] / nr[sel]).max()) if sel.any() else 0.0
     grad_glob = float(np.abs(g - ref_g).max() / max(np.abs(ref_g).max(), 1e-300))
     hit = q["stage"] >= 1
-    ids_equal = bool(np.array_equal(ids >= 0, hit) and np.array_equal(ids[hit], q["tri1"][hit]))
+    ids_ref = m.closest_hit(ray6.cpu().numpy())[1]
+    ok_paths = q["mask"][:, 0]
+    ids_equal = bool(np.array_equal(ids, ids_ref) and np.array_equal(ids >= 0, hit) and np.array_equal(ids[ok_paths], q["tri1"][ok_paths]))
     loss_rel = abs(loss.item() - ref_loss) / max(abs(ref_loss), 1e-300)
     out = {"views": 1, "rays": int(n), "oracle": "oracle/drt_oracle.c (canonical LBVH, float64 chain)", "ids_equal": ids_equal,
            "entry_hits": int(hit.sum()), "valid_paths_gpu": int(n_paths.item()), "valid_paths_oracle": int(q["mask"][:, 0].sum()),

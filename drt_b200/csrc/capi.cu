@@ -64,6 +64,8 @@ struct Tuning {
     int r_grid = 8;       // DRT_R_GRID: blocks per SM of the dense refraction kernels' grids
     bool tile = true;  // DRT_TILE=0: keep scanline batches in drt_ray_loss_step even when the image size is known (A/B switch)
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
+    bool beam = true;  // DRT_BEAM=0: entry query without beam culling of whole pixel tiles (A/B switch)
+    int beam_tpb = 0;  // DRT_BEAM_TPB = 1..32 forces the tiles a warp takes per work fetch (default: by batch size)
     int thresh = 32;
     int pol[3];  // make_policy(thresh, vote) of the three query stages: DRT_FWD_THRESH / DRT_VOTE, per stage DRT_THRESH_Q1.. / DRT_VOTE_Q1..
     int minb = 8;
@@ -102,6 +104,10 @@ struct Tuning {
         if (pl && !strcmp(pl, "1")) prefer_l1 = true;
         const char* bm = getenv("DRT_BWD_MERGE");
         if (bm && (!strcmp(bm, "0") || !strcmp(bm, "1"))) bwd_merge = atoi(bm);
+        const char* bm2 = getenv("DRT_BEAM");
+        if (bm2 && !strcmp(bm2, "0")) beam = false;
+        const char* tp = getenv("DRT_BEAM_TPB");
+        if (tp && atoi(tp) >= 1 && atoi(tp) <= 32) beam_tpb = atoi(tp);
         const char* z = getenv("DRT_BULK_ZERO");
         if (z && !strcmp(z, "0")) bulk = false;
         const char* m = getenv("DRT_Q_MINB");
@@ -193,6 +199,17 @@ TileMap tile_map(int img_w, int img_h, int64_t N, bool dense_outputs)
     for (int lg : shapes)
         if (whole && img_w % (1 << lg) == 0 && img_h % (32 >> lg) == 0) return TileMap{img_w, img_w * img_h, lg};
     return TileMap{0, 0, 3};
+}
+
+// tiles (32 rays) a warp of the beam-culling entry query takes per work fetch: up to 32 (one beam per lane), fewer for
+// small batches so that every warp still gets several fetches (the tail of a persistent kernel is one fetch long)
+int beam_tiles_per_fetch(int64_t N, int warps)
+{
+    if (tuning().beam_tpb) return tuning().beam_tpb;
+    const int64_t tiles = (N + 31) / 32;
+    int tpb = 32;
+    while (tpb > 4 && tiles / tpb < (int64_t)warps * 4) tpb >>= 1;
+    return tpb;
 }
 
 // clamp + count out-of-range indices so that no later kernel can fault on a bad face list
@@ -592,7 +609,7 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
     if ((rc = ensure(b->listA, b->capLA, (size_t)N))) return rc;
     if ((rc = ensure(b->park, b->capPk, 6 * (size_t)N))) return rc;
     if ((rc = ensure(b->listM, b->capLM, (size_t)N))) return rc;
-    if ((rc = ensure(b->listS, b->capLS, (size_t)N))) return rc;
+    if ((rc = ensure(b->listS, b->capLS, (size_t)N))) return rc;  // also holds the int2 list of surviving tiles (N/16 ints) before Q3
     // control block: work counters of Q1,Q2,Q3 + {countL, countM} + {countS, -}
     unsigned long long* ctl = b->work + (size_t)(b->work_slot++ % (kWorkSlots / 8)) * 8;
     CU(cudaMemsetAsync(ctl, 0, 8 * sizeof(unsigned long long), st));
@@ -622,6 +639,16 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
     } while (0)
     // whole images of image_w x image_h pixels that a 32-pixel tile shape divides: a warp's batch becomes a pixel tile
     LossEntryJob j1{rays, b->listA, countL, tile_map(image_w, image_h, N, false)};
+#if DRT_QNODE
+    if (tuning().beam && (pol[0] & 0xff) == 32) {
+        // beam pass over all tiles -> list of the surviving tiles (in listS, free until Q3) -> per-ray entry query over the list
+        int2* tiles = reinterpret_cast<int2*>(b->listS);
+        int* n_tiles = (int*)(ctl + 5);
+        ls_beam_kernel<<<pg, 128, 0, st>>>(b->view(), j1, (int)N, ctl + 0, beam_tiles_per_fetch(N, pg * 4), tiles, n_tiles);
+        ++g_launches;
+        DRT_LAUNCH_Q(ls_q1_tiles_kernel, b->view(), j1, (int)N, tiles, n_tiles, ctl + 6, pol[0]);
+    } else
+#endif
     DRT_LAUNCH_Q(ls_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
     ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park);
     LossExitJob j2{park, b->listA};

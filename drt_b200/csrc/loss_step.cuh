@@ -100,6 +100,7 @@ struct Park {
 // (the warp scheduling model, tools/warp_sim, gives -22 % warp-wide steps for Q1 and -10 % for Q2/Q3).
 struct LossEntryJob {
     static constexpr bool kBulkMiss = false;
+    static constexpr bool kMissWrites = false;  // a missed ray leaves no trace
     __device__ __forceinline__ bool bulk_miss(int, unsigned) { return false; }
     __device__ __forceinline__ void finish(unsigned) {}
     RaySrc rays;
@@ -126,6 +127,21 @@ __global__ void __launch_bounds__(128, MINB) ls_q1_kernel(BvhView B, LossEntryJo
 {
     persistent_query<false>(B, job, N, work, policy);
 }
+
+#if DRT_QNODE
+__global__ void __launch_bounds__(128, 8) ls_beam_kernel(BvhView B, LossEntryJob job, int N, unsigned long long* work, int tpb,
+                                                         int2* __restrict__ tiles, int* __restrict__ n_tiles)
+{
+    beam_pass(B, job, N, work, tpb, tiles, n_tiles);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) ls_q1_tiles_kernel(BvhView B, LossEntryJob job, int N, const int2* __restrict__ tiles,
+                                                                const int* __restrict__ n_tiles, unsigned long long* work, int policy)
+{
+    entry_query_tiles(B, job, N, tiles, n_tiles, work, policy);
+}
+#endif
 
 // ---- R1: refraction at the entry hit, dense over L, refracted ray parked at its slot ---------------
 __global__ void __launch_bounds__(128) ls_r1_kernel(BvhView B, const double* __restrict__ V64, RaySrc rays, double ext_ior,

@@ -175,6 +175,107 @@ __device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float 
 }
 #endif
 
+#if DRT_QNODE
+// ---------------------------------------------------------------------------------------------
+// BEAM = the 32 primary rays of one pixel tile, which share their origin (a pinhole view has ONE camera centre,
+// captured_data.py:38): {o + t d : t >= 0, d in [dmin, dmax]} with per-axis direction intervals over the tile's float32 query
+// rays.  One conservative test of the beam against a box answers "can ANY ray of the tile hit it":
+//   exists t >= 0 with, on every axis,  t dmax >= lo - o  and  t dmin <= hi - o          (each linear in t)
+// which for an axis where every ray points the same way is the ray's own slab test with the NEAR plane divided by the
+// largest |d| and the FAR plane by the smallest -- the same one-FFMA-per-plane form on the quantised planes (node_step), so
+// the same rounding budget applies (3 grid steps of outward margin on every stored plane against <= 1.03 steps of rounding;
+// fl(1/d) is monotonic, so no ray's own bound is ever tighter than the beam's).  An axis whose interval contains 0 (or
+// |d| < 2^-80) is dropped (no constraint): looser, still conservative.  Box tests only CULL: every hit is still decided by the
+// float64 triangle test of the per-ray traversal, so hit ids stay bit-identical.
+// ---------------------------------------------------------------------------------------------
+struct BeamQ {
+    float an[3], cn[3], af[3], cf[3];  // near / far plane: t = q' a + c
+    unsigned sn[3];                    // PRMT selector of the near plane per axis (far = sn ^ 0x22)
+    float E;
+};
+
+__device__ __forceinline__ BeamQ beam_setup(const BvhView& B, float ox, float oy, float oz, const float dmin[3], const float dmax[3])
+{
+    BeamQ q;
+    const float o[3] = {ox, oy, oz};
+    const float tiny = 8.271806125530277e-25f;  // 2^-80
+    float emax = 0.f;
+    bool far_origin = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float s = __uint_as_float(__ldg(B.scene + 11 + k));
+        const float w = __uint_as_float(__ldg(B.scene + 8 + k)) - o[k];
+        if (!(fabsf(w) <= 64.f * 65520.f * s)) far_origin = true;
+        float in, if_;
+        if (dmin[k] > tiny) { in = __fdiv_rn(1.f, dmax[k]); if_ = __fdiv_rn(1.f, dmin[k]); q.sn[k] = 0x7410u; }
+        else if (dmax[k] < -tiny) { in = __fdiv_rn(1.f, dmin[k]); if_ = __fdiv_rn(1.f, dmax[k]); q.sn[k] = 0x7432u; }
+        else { q.an[k] = 0.f; q.cn[k] = -INFINITY; q.af[k] = 0.f; q.cf[k] = INFINITY; q.sn[k] = 0x7410u; continue; }
+        q.an[k] = s * in;
+        q.af[k] = s * if_;
+        const float c_n = w * in, c_f = w * if_;
+        const float m_n = 8388608.f * q.an[k], m_f = 8388608.f * q.af[k];
+        q.cn[k] = c_n - m_n;
+        q.cf[k] = c_f - m_f;
+        emax = fmaxf(emax, fmaxf(fabsf(c_n) + fabsf(m_n), fabsf(c_f) + fabsf(m_f)));
+    }
+    q.E = far_origin ? 4.76837158203125e-07f * emax : 0.f;
+    return q;
+}
+
+// Walks the tree with the beam.  Returns false when the beam touches no leaf box (every ray of the tile misses the mesh);
+// otherwise true and `entry` = the node below which every possible hit of the tile lies: the first node at which the beam
+// enters BOTH children (all siblings passed on the way down were missed by the whole beam), so the per-ray traversals may
+// start there instead of at the root.
+__device__ __forceinline__ bool beam_walk(const BvhView& B, const BeamQ& q, int* stack, int& entry)
+{
+    int sp = 0, node = 0;
+    bool forked = false;
+    entry = 0;
+    const unsigned fx = q.sn[0] ^ 0x22u, fy = q.sn[1] ^ 0x22u, fz = q.sn[2] ^ 0x22u;
+    for (;;) {
+        const uint4* p = B.nodes + (size_t)node * kNodeQuads;
+        const uint4 a = __ldg(p), b = __ldg(p + 1);
+        const float n0 = fmaxf(fmaxf(fmaf(qplane(a.x, q.sn[0]), q.an[0], q.cn[0]), fmaf(qplane(a.z, q.sn[1]), q.an[1], q.cn[1])),
+                               fmaxf(fmaf(qplane(b.x, q.sn[2]), q.an[2], q.cn[2]), 0.f));
+        const float f0 = fminf(fminf(fmaf(qplane(a.x, fx), q.af[0], q.cf[0]), fmaf(qplane(a.z, fy), q.af[1], q.cf[1])),
+                               fmaf(qplane(b.x, fz), q.af[2], q.cf[2]));
+        const float n1 = fmaxf(fmaxf(fmaf(qplane(a.y, q.sn[0]), q.an[0], q.cn[0]), fmaf(qplane(a.w, q.sn[1]), q.an[1], q.cn[1])),
+                               fmaxf(fmaf(qplane(b.y, q.sn[2]), q.an[2], q.cn[2]), 0.f));
+        const float f1 = fminf(fminf(fmaf(qplane(a.y, fx), q.af[0], q.cf[0]), fmaf(qplane(a.w, fy), q.af[1], q.cf[1])),
+                               fmaf(qplane(b.y, fz), q.af[2], q.cf[2]));
+        const bool h0 = n0 <= fmaf(f0, 1.00000095367431640625f, q.E);
+        const bool h1 = n1 <= fmaf(f1, 1.00000095367431640625f, q.E);
+        const int c0 = (int)b.z, c1 = (int)b.w;
+        if ((h0 && c0 < 0) || (h1 && c1 < 0)) {  // a leaf box is touched: the tile may hit
+            if (!forked) entry = node;
+            return true;
+        }
+        if (h0 && h1) {
+            if (!forked) { forked = true; entry = node; }
+            const bool first0 = n0 <= n1;
+            stack[sp++] = first0 ? c1 : c0;
+            node = first0 ? c0 : c1;
+        } else if (h0) node = c0;
+        else if (h1) node = c1;
+        else if (sp) node = stack[--sp];
+        else return false;
+    }
+}
+
+__device__ __forceinline__ float warp_min_f32(float v)
+{
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));  // CREDUX.MIN.F32 (sm_100a)
+    return r;
+}
+__device__ __forceinline__ float warp_max_f32(float v)
+{
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+#endif  // DRT_QNODE
+
 // exact test of the one triangle of a leaf; updates the closest hit (ties -> lowest id)
 __device__ __forceinline__ bool leaf_step(const BvhView& B, const QRay& r, int leaf, double& t_best, int& id_best, float& tmax)
 {

@@ -117,6 +117,123 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
     job.finish(lane);
 }
 
+#if DRT_QNODE
+// Entry query with BEAM CULLING (trace.cuh: BeamQ).  The primary rays of a view share one origin and arrive as pixel tiles,
+// and most of them miss (88 % at C4) after ~10 node steps each.  Two launches:
+//  beam_pass: a warp takes `tpb` tiles (32 rays each) per work fetch;
+//   A  lane l loads ray l of tile t = 0..tpb-1 in turn; warp min / max reductions (CREDUX.F32) give lane t the direction
+//      intervals of tile t, a vote tells whether all its rays start at the same point (checked per tile on the data itself --
+//      no promise from the caller; tiles that fail it are traced ray by ray from the root);
+//   B  every lane walks the tree with ITS tile's beam: no leaf box touched -> the 32 rays of the tile retire as misses for
+//      the price of one traversal; otherwise the tile is appended to a list together with its entry point, the first node
+//      where the beam forks;
+//  entry_query_tiles: persistent warps fetch ONE listed tile at a time (a tile is the unit of dynamic balancing: a fused
+//      variant that traced the surviving tiles of its own 1024-ray batch in place measured slower than no culling at all --
+//      batches whose 32 tiles all survive are 30x longer than empty ones and the kernel ends in their tail) and trace its
+//      rays exactly as before (walk_vote / drain), starting at the entry point.
+// Hit ids are unchanged (the beam only removes box tests that every ray of the tile would fail).
+template <class Job>
+__device__ __forceinline__ void beam_pass(const BvhView& B, Job& job, int total, unsigned long long* work, int tpb,
+                                          int2* __restrict__ tiles, int* __restrict__ n_tiles)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    int stack[kStackDepth];
+    for (;;) {
+        unsigned long long base64 = 0;
+        if (lane == 0) base64 = atomicAdd(work, (unsigned long long)(32 * tpb));
+        base64 = __shfl_sync(FULL, base64, 0);
+        if (base64 >= (unsigned long long)total) break;
+        const int base = (int)base64;
+        // ---- A: direction intervals and the common origin of every tile of the batch --------------------------
+        float dmn[3] = {INFINITY, INFINITY, INFINITY}, dmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        float box = 0.f, boy = 0.f, boz = 0.f;
+        bool has_rays = false, shared_origin = false;
+#pragma unroll 4
+        for (int t = 0; t < tpb; ++t) {
+            const int item = base + 32 * t + (int)lane;
+            d3 o, d;
+            const bool act = item < total && job.load(item, o, d);
+            const QRay r = act ? cast_ray(o, d) : QRay{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const unsigned am = __ballot_sync(FULL, act);
+            const int src = am ? __ffs(am) - 1 : 0;
+            const float ox = __shfl_sync(FULL, r.ox, src), oy = __shfl_sync(FULL, r.oy, src), oz = __shfl_sync(FULL, r.oz, src);
+            const bool same = __all_sync(FULL, !act || (r.ox == ox && r.oy == oy && r.oz == oz));
+            const float a0 = warp_min_f32(act ? r.dx : INFINITY), a1 = warp_min_f32(act ? r.dy : INFINITY), a2 = warp_min_f32(act ? r.dz : INFINITY);
+            const float b0 = warp_max_f32(act ? r.dx : -INFINITY), b1 = warp_max_f32(act ? r.dy : -INFINITY), b2 = warp_max_f32(act ? r.dz : -INFINITY);
+            if ((int)lane == t) {
+                dmn[0] = a0; dmn[1] = a1; dmn[2] = a2;
+                dmx[0] = b0; dmx[1] = b1; dmx[2] = b2;
+                box = ox; boy = oy; boz = oz;
+                has_rays = am != 0u;
+                shared_origin = same;
+            }
+        }
+        // ---- B: one beam per lane ------------------------------------------------------------------------------
+        bool keep = false;
+        int entry = 0;
+        if (has_rays) {
+            keep = true;  // different origins inside the tile: no beam, every ray from the root
+            if (shared_origin && B.nTris > 0) {
+                const BeamQ bq = beam_setup(B, box, boy, boz, dmn, dmx);
+                keep = beam_walk(B, bq, stack, entry);
+            }
+        }
+        const int slot = warp_append<>(n_tiles, keep);
+        if (slot >= 0) tiles[slot] = make_int2(base + 32 * (int)lane, entry);
+        if (Job::kMissWrites) {  // culled tiles: their rays retire as misses (dense outputs are zero-filled)
+            unsigned culled = __ballot_sync(FULL, has_rays && !keep);
+            while (culled) {
+                const int t = __ffs(culled) - 1;
+                culled &= culled - 1;
+                const int item = base + 32 * t + (int)lane;
+                if (item < total) job.retire(item, -1, INFINITY);
+            }
+        }
+    }
+}
+
+template <class Job>
+__device__ __forceinline__ void entry_query_tiles(const BvhView& B, Job& job, int total, const int2* __restrict__ tiles,
+                                                  const int* __restrict__ n_tiles, unsigned long long* work, int policy)
+{
+    const int vote = policy >> 8;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const int n = *n_tiles;
+    int stack[kStackDepth];
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(work, 1ull);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= (unsigned long long)n) break;
+        const int2 tl = __ldg(tiles + k);
+        const int item = tl.x + (int)lane;
+        d3 o, d;
+        RayQ q;
+        float tmax = INFINITY;
+        double t_best = INFINITY;
+        int id_best = -1, node = kDone, sp = 0, nd = 0;
+        const bool act = item < total && job.load(item, o, d);
+        if (act && B.nTris > 0) {
+            q = ray_setup(B, cast_ray(o, d));
+            node = tl.y;
+        } else {
+            q = ray_setup(B, QRay{0.f, 0.f, 0.f, 1.f, 1.f, 1.f});
+        }
+        for (;;) {
+            if (vote) walk_vote(B, q, tmax, node, stack, sp, nd, vote);
+            else walk(B, q, tmax, node, stack, sp, nd);
+            drain<false>(B, q.r, stack, nd, t_best, id_best, tmax);
+            if (!__any_sync(FULL, node != kDone)) break;
+        }
+        if (act) job.retire(item, id_best, t_best);
+    }
+    job.finish(lane);
+}
+#endif  // DRT_QNODE
+
+
 // ---- Q1 ------------------------------------------------------------------------------------------
 // 32 x 24 B of zeros, the source of the bulk zero-fill; one per block, written once, read by the async proxy
 struct ZeroTile {
@@ -133,6 +250,7 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigne
 
 struct EntryJob {
     static constexpr bool kBulkMiss = true;
+    static constexpr bool kMissWrites = true;  // a missed ray has outputs (zeros)
     const ZeroTile* zeros;  // shared memory; nullptr disables the bulk path (unaligned outputs)
     bool issued;
     const double* __restrict__ origin;

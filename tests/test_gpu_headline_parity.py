@@ -113,10 +113,14 @@ def test_full_c4_view_vs_oracle(cuda_device):
     assert np.array_equal(oo.cpu().numpy().view(np.uint64), q["out_ori"].view(np.uint64))
     assert np.array_equal(od.cpu().numpy().view(np.uint64), q["out_dir"].view(np.uint64))
     # entry-hit ids of all 691 200 primary rays
-    _, ID = sc.optix_mesh.intersect(torch.cat([og.float(), dg.float()], dim=1))
+    ray6 = torch.cat([og.float(), dg.float()], dim=1)
+    T, ID = sc.optix_mesh.intersect(ray6)
+    T_ref, ID_ref = m.closest_hit(ray6.cpu().numpy())
     ids = ID.cpu().numpy()
+    assert np.array_equal(ids, ID_ref) and np.array_equal(T.cpu().numpy().view(np.uint32), T_ref.view(np.uint32))
     assert np.array_equal(ids >= 0, q["stage"] >= 1)
-    assert np.array_equal(ids[ids >= 0], q["tri1"][ids >= 0])
+    ok = q["mask"][:, 0]                      # the oracle's forward records tri1 for the valid paths
+    assert np.array_equal(ids[ok], q["tri1"][ok])
 
     tg = losses.SparseTargets.from_dense(torch.tensor(screen, device=cuda_device), torch.tensor(valid, device=cuda_device))
     for image_size in ((resy, resx), None):             # 4x8 pixel tiles / scanline batches

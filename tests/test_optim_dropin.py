@@ -34,7 +34,7 @@ class _StubOptixMesh:
         return 0
 
 
-def _replay(Render, path, tmp_path, n_pass, n_iter, loss_fn):
+def _replay(Render, path, tmp_path, n_pass, n_iter, loss_fn, lr=0.05):
     """optim.py:145-219 with MeshLab replaced by a file copy (the remesher is an external binary, absent here)."""
     from drt_b200 import plyio
     scene = Render.Scene(str(path))
@@ -47,7 +47,8 @@ def _replay(Render, path, tmp_path, n_pass, n_iter, loss_fn):
         scene.update_mesh(str(remeshed))                                 # optim.py:52
         init_vertices = scene.vertices                                   # optim.py:166
         parameter = torch.zeros(init_vertices.shape, dtype=torch.float64, requires_grad=True, device=init_vertices.device)
-        opt = torch.optim.SGD([parameter], lr=0.05, momentum=0.9, nesterov=True)
+        parameter.register_hook(lambda g: torch.nan_to_num(g, nan=0.0).clamp(-1.0, 1.0))   # optim.py:155-162, 168
+        opt = torch.optim.SGD([parameter], lr=lr, momentum=0.9, nesterov=True)
         for _ in range(n_iter):
             opt.zero_grad()
             vertices = init_vertices + parameter                         # optim.py:202
@@ -129,10 +130,11 @@ def test_optim_py_call_sequence_on_gpu(tmp_path, cuda_device):
         sm_loss = (-torch.log(1 + scene.dihedral_angle())).sum()
         return 40 * 217.5 / data.resy / data.resy * ray_loss + 2e-3 * 217.5 / data.resy * vh_loss + 0.08 * scene.mean_len / 10 * sm_loss
 
-    scene, exported, final = _replay(Render, path, tmp_path, n_pass=2, n_iter=4, loss_fn=all_loss)
+    scene, exported, final = _replay(Render, path, tmp_path, n_pass=2, n_iter=4, loss_fn=all_loss, lr=0.5)
     assert np.abs(exported[0] - v).max() <= 1e-5
     moved = np.abs(exported[1] - exported[0]).max()
-    assert moved > 1e-4, "pass 1 was remeshed from the INITIAL mesh: scene.mesh did not follow update_verticex"
+    assert moved > 1e-3, moved
+    assert moved > 1e-3, "pass 1 was remeshed from the INITIAL mesh: scene.mesh did not follow update_verticex"
     now = scene.vertices.detach().cpu().numpy()
     assert np.abs(final - now).max() <= 1e-5 * max(1.0, np.abs(now).max())
     assert np.abs(final - exported[1]).max() > 1e-4
