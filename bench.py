@@ -408,6 +408,7 @@ def run_b200(args):
     value = n_total / (ms_per_step * 1e-3)
     loss_val = float(loss_buf.item())
     grad_norm = float(V.grad.norm().item())
+    stage_counts = scene.optix_mesh.last_counts() if args.loss_path == "step" else None
 
     # ---- parity of the timed workload (rank 0, outside the timed region) and of the collective ----------------
     parity = ar_check = None
@@ -699,7 +700,7 @@ def run_b200(args):
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "e2e": e2e, "e2e_reference_layout": e2e_ref_layout, "e2e_pinhole": e2e_pinhole, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "loss": loss_val, "grad_norm": grad_norm,
-            "parity_check": parity, "allreduce_check": ar_check, "shard": {"policy": args.shard if world > 1 else "none", "skew": shard_skew},
+            "stage_counts_rank0": stage_counts, "parity_check": parity, "allreduce_check": ar_check, "shard": {"policy": args.shard if world > 1 else "none", "skew": shard_skew},
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -21,6 +21,7 @@ SIGNATURES = {
     "drt_bvh_update_vert": (C.c_int, [_vp, _vp, _vp, _i32, C.c_int, _vp]),
     "drt_bvh_bad_indices": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
     "drt_bvh_info": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "drt_bvh_last_counts": (C.c_int, [_vp, _vp, C.POINTER(_i64)]),
     "drt_bvh_set_image_size": (C.c_int, [_vp, _i32, _i32]),
     "drt_closest_hit": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "drt_trace_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

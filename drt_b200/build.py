@@ -43,5 +43,37 @@ def build(force=False, verbose=False):
     return SO
 
 
+def load_torch_plugin():
+    """Imports the in-tree compiled plugin (_C/optix_b200/optix_b200.so), building it first when absent or stale."""
+    import importlib.util
+    import torch  # noqa: F401  (the extension links against libtorch)
+    so = os.path.join(OUT_DIR, "optix_b200", "optix_b200.so")
+    src = os.path.join(SRC, "optix_extend_b200.cpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src) or needs_build():
+        return build_torch_plugin()
+    spec = importlib.util.spec_from_file_location("optix_b200", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def build_torch_plugin(verbose=False):
+    """The reference's pybind plugin class (optix_extend.cpp:77-83) as a compiled torch extension over the C ABI
+    (csrc/optix_extend_b200.cpp, the binding of INTEGRATION.md section 4): built IN-TREE into _C/optix_b200/ so that it
+    travels to the GPU box; returns the imported module (`module.optix_mesh`)."""
+    import torch.utils.cpp_extension as ce
+    build()
+    out = os.path.join(OUT_DIR, "optix_b200")
+    os.makedirs(out, exist_ok=True)
+    env_cc = {k: os.environ.pop(k) for k in ("CC", "CXX") if k in os.environ}
+    try:
+        return ce.load(name="optix_b200", sources=[os.path.join(SRC, "optix_extend_b200.cpp")],
+                       extra_include_paths=[os.path.join(os.path.dirname(HERE), "include")],
+                       extra_ldflags=[f"-L{OUT_DIR}", "-ldrt_b200", f"-Wl,-rpath,{OUT_DIR}", "-Wl,-rpath,$ORIGIN/.."],
+                       build_directory=out, with_cuda=True, verbose=verbose)
+    finally:
+        os.environ.update(env_cc)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -65,6 +65,7 @@ struct Tuning {
     bool tile = true;  // DRT_TILE=0: keep scanline batches in drt_ray_loss_step even when the image size is known (A/B switch)
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
     bool beam = true;  // DRT_BEAM=0: entry query without beam culling of whole pixel tiles (A/B switch)
+    int beam_steps = 1 << 30;  // DRT_BEAM_STEPS: node steps after which an undecided beam is kept
     int beam_tpb = 0;  // DRT_BEAM_TPB = 1..32 forces the tiles a warp takes per work fetch (default: by batch size)
     int thresh = 32;
     int pol[3];  // make_policy(thresh, vote) of the three query stages: DRT_FWD_THRESH / DRT_VOTE, per stage DRT_THRESH_Q1.. / DRT_VOTE_Q1..
@@ -106,6 +107,8 @@ struct Tuning {
         if (bm && (!strcmp(bm, "0") || !strcmp(bm, "1"))) bwd_merge = atoi(bm);
         const char* bm2 = getenv("DRT_BEAM");
         if (bm2 && !strcmp(bm2, "0")) beam = false;
+        const char* bs = getenv("DRT_BEAM_STEPS");
+        if (bs && atoi(bs) >= 1) beam_steps = atoi(bs);
         const char* tp = getenv("DRT_BEAM_TPB");
         if (tp && atoi(tp) >= 1 && atoi(tp) <= 32) beam_tpb = atoi(tp);
         const char* z = getenv("DRT_BULK_ZERO");
@@ -148,6 +151,8 @@ struct drt_bvh {
     int* listS = nullptr;      size_t capLS = 0; // loss step: slots of L whose exit ray is unoccluded (the valid paths)
     int* tbucket = nullptr;    size_t capTb = 0; // loss step: bucket table of the sparse screen targets
     unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
+    unsigned long long* last_ctl = nullptr;      // control block of the latest drt_ray_loss_step (drt_bvh_last_counts)
+    int64_t last_tiles = 0;                      // its number of 32-ray tiles (0: no beam pass)
     int work_slot = 0;
     int fused_blocks_per_sm = 0;                 // co-resident blocks of wf_fused_kernel<8> (0: no cooperative launch)
     int fused6_blocks_per_sm = 0;                // same for the 80-register variant
@@ -433,6 +438,21 @@ int drt_bvh_bad_indices(const drt_bvh* b, void* stream, int* out)
     return DRT_OK;
 }
 
+int drt_bvh_last_counts(const drt_bvh* b, void* stream, int64_t out[6])
+{
+    if (!b || !out) return fail(DRT_ERR_INVALID, "drt_bvh_last_counts: null argument");
+    for (int k = 0; k < 6; ++k) out[k] = 0;
+    if (!b->last_ctl) return DRT_OK;
+    DeviceGuard g(b->device);
+    unsigned long long h[8];
+    CU(cudaMemcpyAsync(h, b->last_ctl, sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    const int* c = reinterpret_cast<const int*>(h);
+    out[0] = c[6]; out[1] = c[7]; out[2] = c[8];   // entry hits, survivors of both refractions, valid paths
+    out[3] = b->last_tiles; out[4] = b->last_tiles ? c[10] : 0;  // tiles seen / kept by the beam pass
+    return DRT_OK;
+}
+
 int drt_closest_hit(const drt_bvh* b, const float* ray6, int64_t N, float* T, int32_t* ID, int64_t strideT, int64_t strideID, void* stream)
 {
     if (!b) return fail(DRT_ERR_INVALID, "drt_closest_hit: null handle");
@@ -616,6 +636,8 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
     int* countL = (int*)(ctl + 3);
     int* countM = countL + 1;
     int* countS = (int*)(ctl + 4);
+    b->last_ctl = ctl;
+    b->last_tiles = 0;
     const int* pol = tuning().pol;
     const int minb = tuning().minb;
     const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * tuning().r_grid);
@@ -644,7 +666,8 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
         // beam pass over all tiles -> list of the surviving tiles (in listS, free until Q3) -> per-ray entry query over the list
         int2* tiles = reinterpret_cast<int2*>(b->listS);
         int* n_tiles = (int*)(ctl + 5);
-        ls_beam_kernel<<<pg, 128, 0, st>>>(b->view(), j1, (int)N, ctl + 0, beam_tiles_per_fetch(N, pg * 4), tiles, n_tiles);
+        b->last_tiles = (N + 31) / 32;
+        ls_beam_kernel<<<pg, 128, 0, st>>>(b->view(), j1, (int)N, ctl + 0, beam_tiles_per_fetch(N, pg * 4), tuning().beam_steps, tiles, n_tiles);
         ++g_launches;
         DRT_LAUNCH_Q(ls_q1_tiles_kernel, b->view(), j1, (int)N, tiles, n_tiles, ctl + 6, pol[0]);
     } else

@@ -125,21 +125,23 @@ struct LossEntryJob {
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) ls_q1_kernel(BvhView B, LossEntryJob job, int N, unsigned long long* work, int policy)
 {
-    persistent_query<false>(B, job, N, work, policy);
+    DRT_QUERY_STACK(stack);
+    persistent_query<false>(B, job, N, work, policy, stack);
 }
 
 #if DRT_QNODE
 __global__ void __launch_bounds__(128, 8) ls_beam_kernel(BvhView B, LossEntryJob job, int N, unsigned long long* work, int tpb,
-                                                         int2* __restrict__ tiles, int* __restrict__ n_tiles)
+                                                         int max_steps, int2* __restrict__ tiles, int* __restrict__ n_tiles)
 {
-    beam_pass(B, job, N, work, tpb, tiles, n_tiles);
+    beam_pass(B, job, N, work, tpb, max_steps, tiles, n_tiles);
 }
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) ls_q1_tiles_kernel(BvhView B, LossEntryJob job, int N, const int2* __restrict__ tiles,
                                                                 const int* __restrict__ n_tiles, unsigned long long* work, int policy)
 {
-    entry_query_tiles(B, job, N, tiles, n_tiles, work, policy);
+    DRT_QUERY_STACK(stack);
+    entry_query_tiles(B, job, N, tiles, n_tiles, work, policy, stack);
 }
 #endif
 
@@ -180,7 +182,8 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB) ls_q2_kernel(BvhView B, LossExitJob job, const int* __restrict__ countL,
                                                           unsigned long long* work, int policy)
 {
-    persistent_query<false>(B, job, *countL, work, policy);
+    DRT_QUERY_STACK(stack);
+    persistent_query<false>(B, job, *countL, work, policy, stack);
 }
 
 // ---- R2: refraction at the exit hit; exit ray parked in place, surviving SLOTS appended to M ---------
@@ -231,7 +234,8 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB) ls_q3_kernel(BvhView B, LossOcclusionJob job, const int* __restrict__ countM,
                                                           unsigned long long* work, int policy)
 {
-    persistent_query<true>(B, job, *countM, work, policy);
+    DRT_QUERY_STACK(stack);
+    persistent_query<true>(B, job, *countM, work, policy, stack);
 }
 
 // ---- loss + backward over the valid paths -------------------------------------------------------------

@@ -50,7 +50,7 @@ __device__ __forceinline__ int warp_append(int* __restrict__ counter, bool pred)
 __host__ __device__ constexpr int make_policy(int thresh, int vote) { return thresh | (vote << 8); }
 
 template <bool ANY, class Job>
-__device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int total, unsigned long long* work, int policy)
+__device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int total, unsigned long long* work, int policy, QueryStack& stack)
 {
     const int thresh = policy & 0xff, vote = policy >> 8;
     const unsigned FULL = 0xffffffffu;
@@ -63,7 +63,6 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
     float tmax = 0.f;
     double t_best = 0.0;
     int id_best = -1, node = kDone, sp = 0, nd = 0;
-    int stack[kStackDepth];
 
     for (;;) {
 #pragma unroll 1
@@ -99,7 +98,7 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
         for (;;) {
             if (vote) walk_vote(B, q, tmax, node, stack, sp, nd, vote);
             else walk(B, q, tmax, node, stack, sp, nd);
-            if (drain<ANY>(B, q.r, stack, nd, t_best, id_best, tmax)) { node = kDone; sp = 0; }
+            if (drain<ANY>(B, q.r, stack, nd, t_best, id_best, tmax)) { node = kDone; stack.reset(sp); }
             unsigned fin = __ballot_sync(FULL, item >= 0 && node == kDone);
             if (__popc(fin) >= need) break;
         }
@@ -121,19 +120,19 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
 // Entry query with BEAM CULLING (trace.cuh: BeamQ).  The primary rays of a view share one origin and arrive as pixel tiles,
 // and most of them miss (88 % at C4) after ~10 node steps each.  Two launches:
 //  beam_pass: a warp takes `tpb` tiles (32 rays each) per work fetch;
-//   A  lane l loads ray l of tile t = 0..tpb-1 in turn; warp min / max reductions (CREDUX.F32) give lane t the direction
-//      intervals of tile t, a vote tells whether all its rays start at the same point (checked per tile on the data itself --
-//      no promise from the caller; tiles that fail it are traced ray by ray from the root);
+//   A  lane t reads the 32 rays of tile t: direction intervals, and whether all of them start at the same point (checked
+//      per tile on the data itself -- no promise from the caller; tiles that fail it are traced ray by ray from the root);
 //   B  every lane walks the tree with ITS tile's beam: no leaf box touched -> the 32 rays of the tile retire as misses for
 //      the price of one traversal; otherwise the tile is appended to a list together with its entry point, the first node
-//      where the beam forks;
+//      where the beam forks.  A beam that is still undecided after `max_steps` node steps is kept (the lanes of a warp wait
+//      for its slowest beam, and the undecided ones hug the silhouette);
 //  entry_query_tiles: persistent warps fetch ONE listed tile at a time (a tile is the unit of dynamic balancing: a fused
 //      variant that traced the surviving tiles of its own 1024-ray batch in place measured slower than no culling at all --
 //      batches whose 32 tiles all survive are 30x longer than empty ones and the kernel ends in their tail) and trace its
 //      rays exactly as before (walk_vote / drain), starting at the entry point.
 // Hit ids are unchanged (the beam only removes box tests that every ray of the tile would fail).
 template <class Job>
-__device__ __forceinline__ void beam_pass(const BvhView& B, Job& job, int total, unsigned long long* work, int tpb,
+__device__ __forceinline__ void beam_pass(const BvhView& B, Job& job, int total, unsigned long long* work, int tpb, int max_steps,
                                           int2* __restrict__ tiles, int* __restrict__ n_tiles)
 {
     const unsigned FULL = 0xffffffffu;
@@ -145,28 +144,24 @@ __device__ __forceinline__ void beam_pass(const BvhView& B, Job& job, int total,
         base64 = __shfl_sync(FULL, base64, 0);
         if (base64 >= (unsigned long long)total) break;
         const int base = (int)base64;
-        // ---- A: direction intervals and the common origin of every tile of the batch --------------------------
+        // ---- A: direction intervals and the common origin of the lane's own tile (32 rays, read in turn: neighbouring lanes
+        //      read neighbouring tiles, every sector a lane touches is used up by its next loads) ------------------------
         float dmn[3] = {INFINITY, INFINITY, INFINITY}, dmx[3] = {-INFINITY, -INFINITY, -INFINITY};
         float box = 0.f, boy = 0.f, boz = 0.f;
-        bool has_rays = false, shared_origin = false;
+        bool has_rays = false, shared_origin = true;
+        if ((int)lane < tpb) {
+            const int first = base + 32 * (int)lane;
 #pragma unroll 4
-        for (int t = 0; t < tpb; ++t) {
-            const int item = base + 32 * t + (int)lane;
-            d3 o, d;
-            const bool act = item < total && job.load(item, o, d);
-            const QRay r = act ? cast_ray(o, d) : QRay{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            const unsigned am = __ballot_sync(FULL, act);
-            const int src = am ? __ffs(am) - 1 : 0;
-            const float ox = __shfl_sync(FULL, r.ox, src), oy = __shfl_sync(FULL, r.oy, src), oz = __shfl_sync(FULL, r.oz, src);
-            const bool same = __all_sync(FULL, !act || (r.ox == ox && r.oy == oy && r.oz == oz));
-            const float a0 = warp_min_f32(act ? r.dx : INFINITY), a1 = warp_min_f32(act ? r.dy : INFINITY), a2 = warp_min_f32(act ? r.dz : INFINITY);
-            const float b0 = warp_max_f32(act ? r.dx : -INFINITY), b1 = warp_max_f32(act ? r.dy : -INFINITY), b2 = warp_max_f32(act ? r.dz : -INFINITY);
-            if ((int)lane == t) {
-                dmn[0] = a0; dmn[1] = a1; dmn[2] = a2;
-                dmx[0] = b0; dmx[1] = b1; dmx[2] = b2;
-                box = ox; boy = oy; boz = oz;
-                has_rays = am != 0u;
-                shared_origin = same;
+            for (int j = 0; j < 32; ++j) {
+                d3 o, d;
+                if (first + j < total && job.load(first + j, o, d)) {
+                    const QRay r = cast_ray(o, d);
+                    if (!has_rays) { box = r.ox; boy = r.oy; boz = r.oz; has_rays = true; }
+                    shared_origin = shared_origin && r.ox == box && r.oy == boy && r.oz == boz;
+                    dmn[0] = fminf(dmn[0], r.dx); dmn[1] = fminf(dmn[1], r.dy); dmn[2] = fminf(dmn[2], r.dz);
+                    dmx[0] = fmaxf(dmx[0], r.dx); dmx[1] = fmaxf(dmx[1], r.dy); dmx[2] = fmaxf(dmx[2], r.dz);
+                    if (!(r.dx == r.dx && r.dy == r.dy && r.dz == r.dz)) shared_origin = false;  // a NaN direction: no beam
+                }
             }
         }
         // ---- B: one beam per lane ------------------------------------------------------------------------------
@@ -176,7 +171,7 @@ __device__ __forceinline__ void beam_pass(const BvhView& B, Job& job, int total,
             keep = true;  // different origins inside the tile: no beam, every ray from the root
             if (shared_origin && B.nTris > 0) {
                 const BeamQ bq = beam_setup(B, box, boy, boz, dmn, dmx);
-                keep = beam_walk(B, bq, stack, entry);
+                keep = beam_walk(B, bq, stack, entry, max_steps);
             }
         }
         const int slot = warp_append<>(n_tiles, keep);
@@ -195,13 +190,12 @@ __device__ __forceinline__ void beam_pass(const BvhView& B, Job& job, int total,
 
 template <class Job>
 __device__ __forceinline__ void entry_query_tiles(const BvhView& B, Job& job, int total, const int2* __restrict__ tiles,
-                                                  const int* __restrict__ n_tiles, unsigned long long* work, int policy)
+                                                  const int* __restrict__ n_tiles, unsigned long long* work, int policy, QueryStack& stack)
 {
     const int vote = policy >> 8;
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const int n = *n_tiles;
-    int stack[kStackDepth];
     for (;;) {
         unsigned long long k = 0;
         if (lane == 0) k = atomicAdd(work, 1ull);
@@ -308,7 +302,8 @@ __global__ void __launch_bounds__(128, MINB) wf_q1_kernel(BvhView B, EntryJob jo
     __syncthreads();
     if (job.zeros) job.zeros = &zt;
     job.issued = false;
-    persistent_query<false>(B, job, N, work, policy);
+    DRT_QUERY_STACK(stack);
+    persistent_query<false>(B, job, N, work, policy, stack);
 }
 
 // ---- R1: refraction at the entry hit, dense over L ------------------------------------------------
@@ -368,7 +363,8 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB) wf_q2_kernel(BvhView B, ExitJob job, const int* __restrict__ countL,
                                                     unsigned long long* work, int policy)
 {
-    persistent_query<false>(B, job, *countL, work, policy);
+    DRT_QUERY_STACK(stack);
+    persistent_query<false>(B, job, *countL, work, policy, stack);
 }
 
 // ---- R2: refraction at the exit hit, dense over L; survivors -> M ---------------------------------
@@ -446,7 +442,8 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB) wf_q3_kernel(BvhView B, OcclusionJob job, const int* __restrict__ countM,
                                                     unsigned long long* work, int policy)
 {
-    persistent_query<true>(B, job, *countM, work, policy);
+    DRT_QUERY_STACK(stack);
+    persistent_query<true>(B, job, *countM, work, policy, stack);
 }
 
 // ---- all five stages in ONE cooperative launch ------------------------------------------------------
@@ -484,23 +481,24 @@ __global__ void __launch_bounds__(128, MINB) wf_fused_kernel(FwdArgs a)
     __syncthreads();
     int* countL = reinterpret_cast<int*>(a.ctl + 3);
     int* countM = countL + 1;
+    DRT_QUERY_STACK(stack);
     {
         EntryJob j{a.bulk ? &zt : nullptr, false, a.origin, a.dir, a.out_ori, a.out_dir, a.mask3, a.hit1, a.L, countL, a.tiles};
-        persistent_query<false>(a.B, j, a.N, a.ctl + 0, a.policy[0]);
+        persistent_query<false>(a.B, j, a.N, a.ctl + 0, a.policy[0], stack);
     }
     grid.sync();
     r1_body(a.B, a.V64, a.origin, a.dir, a.ext_ior, a.int_ior, a.out_ori, a.out_dir, a.mask3, a.L, countL);
     grid.sync();
     {
         ExitJob j{a.out_ori, a.out_dir, a.L};
-        persistent_query<false>(a.B, j, *(volatile int*)countL, a.ctl + 1, a.policy[1]);
+        persistent_query<false>(a.B, j, *(volatile int*)countL, a.ctl + 1, a.policy[1], stack);
     }
     grid.sync();
     r2_body(a.B, a.V64, a.ext_ior, a.int_ior, a.out_ori, a.out_dir, a.mask3, a.L, countL, a.M, countM);
     grid.sync();
     {
         OcclusionJob j{a.out_ori, a.out_dir, a.mask3, a.M, a.rec, a.rec_count};
-        persistent_query<true>(a.B, j, *(volatile int*)countM, a.ctl + 2, a.policy[2]);
+        persistent_query<true>(a.B, j, *(volatile int*)countM, a.ctl + 2, a.policy[2], stack);
     }
 }
 

@@ -108,6 +108,13 @@ class optix_mesh:  # noqa: N801  (name fixed by the reference, optix_extend.cpp:
         keys = ("n_faces", "n_verts", "n_nodes", "built", "node_bytes", "tri_bytes", "builds", "refits")
         return dict(zip(keys, list(a)))
 
+    def last_counts(self):
+        """stage counters of the latest fused ray-loss step (synchronises): entry hits, alive after both refractions, valid
+        paths, tiles seen / kept by the beam pass"""
+        a = (C.c_int64 * 6)()
+        _lib.call("drt_bvh_last_counts", self._h, _stream_ptr(self.device), a)
+        return dict(zip(("entry_hits", "alive", "valid_paths", "tiles", "tiles_kept"), list(a)))
+
     def bad_indices(self):
         out = C.c_int(0)
         _lib.call("drt_bvh_bad_indices", self._h, _stream_ptr(self.device), C.byref(out))

@@ -86,6 +86,12 @@ DRT_API int drt_bvh_bad_indices(const drt_bvh* bvh, void* stream, int* out);
  * [6]=builds so far, [7]=refits so far.  Host call, no device sync. */
 DRT_API int drt_bvh_info(const drt_bvh* bvh, int64_t info[8]);
 
+/* Stage counters of the latest drt_ray_loss_step on this handle (synchronises `stream`; diagnostics for bench.py, no
+ * reference counterpart -- the reference's equivalents are the lengths of the Ray sets after each Ray.select,
+ * DiffRender.py:538-544): out = {entry hits, rays alive after both refractions, valid paths, 32-ray tiles seen by the
+ * beam pass, tiles it kept, 0}. */
+DRT_API int drt_bvh_last_counts(const drt_bvh* bvh, void* stream, int64_t out[6]);
+
 /*
  * Replaces optix_mesh::intersect(Ray) -- optix_extend.cpp:29-57 (RTP_QUERY_TYPE_CLOSEST,
  * RTP_BUFFER_FORMAT_RAY_ORIGIN_DIRECTION in, RTP_BUFFER_FORMAT_HIT_T_TRIID out).
