@@ -587,6 +587,25 @@ def run_b200(args):
             assert abs(loss_host.item() - loss_val) <= tol * max(1.0, abs(loss_val)), (loss_host.item(), loss_val)
             return te.item() / k_e2e, k_e2e
 
+        # pinned host -> device copy bandwidth of this GPU, measured now (256 MiB, best of 4): the ceiling of any e2e number
+        probe = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        h2d_peak = 0.0
+        for _ in range(4):
+            pa, pb = ev(), ev()
+            pa.record()
+            probe_d.copy_(probe, non_blocking=True)
+            pb.record()
+            torch.cuda.synchronize(dev)
+            h2d_peak = max(h2d_peak, probe.numel() / (pa.elapsed_time(pb) * 1e-3) / 1e9)
+        del probe, probe_d
+
+        def pcie(entry, h2d_bytes):
+            entry["h2d_gbs_per_gpu"] = h2d_bytes / world / (entry["ms_per_step"] * 1e-3) / 1e9
+            entry["h2d_peak_gbs_measured"] = h2d_peak
+            entry["pcie_frac"] = entry["h2d_gbs_per_gpu"] / h2d_peak if h2d_peak else None
+            return entry
+
         d2h = int(world * (nV * 24 + 8))
         up, comp, h2d, nch = make_reference_layout()
         ms, k_e2e = time_e2e(up, comp, nch)
@@ -594,6 +613,7 @@ def run_b200(args):
                           "d2h_bytes_per_step": d2h,
                           "note": "per-view H2D of the reference's dense view tensors (origin/ray_dir/screen_pixel f64 [N,3] + valid, "
                                   "73 B per ray) from pinned host memory, double-buffered on a copy stream; D2H of grad_V and loss"}
+        pcie(e2e_ref_layout, h2d)
         del up, comp
         torch.cuda.empty_cache()
         if args.loss_path == "step":
@@ -604,6 +624,7 @@ def run_b200(args):
                    "note": "per-view H2D from pinned host memory of the loader's lossless compact view (captured_data.CompactView: "
                            "one origin row per pinhole view, ray_dir f64 [N,3], int32 index + f64 screen point of the measured pixels "
                            "only), %d views per chunk, double-buffered on a copy stream; losses.ray_loss_view per chunk; D2H of grad_V and loss" % max(1, args.e2e_chunk)}
+            pcie(e2e, h2d)
             del up, comp
             torch.cuda.empty_cache()
             if world == 1:
@@ -674,18 +695,49 @@ def run_b200(args):
             b_fwd = cnt["bytes_per_ray"]["fwd"]
             b_tot = cnt["bytes_per_ray"]["total"]
             ach = b_fwd * (n_total / world) / (t_fwd_ms * 1e-3) / 1e9
-            traffic = None
+            # ncu-derived figures (one --set full capture of an 8-view step, profiles/ncu_summary.json) are used only when
+            # they were captured from THESE kernels: the summary records a hash of the kernel sources
+            traffic = ncu = None
+            ncu_note = "no ncu summary"
             try:
-                per_ray = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["loss_step_fwd" if args.loss_path == "step" else "trace_fwd"]["dram_bytes_per_ray"]
-                traffic = per_ray * (n_total / world)  # ncu --set full capture, scaled to this launch's ray count
+                from drt_b200 import build as _build
+                rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["loss_step_fwd" if args.loss_path == "step" else "trace_fwd"]
+                if rec.get("source_hash") == _build.source_hash():
+                    ncu, ncu_note = rec, "ncu capture %s of these kernels (source hash %s)" % (rec.get("from"), rec.get("source_hash"))
+                    traffic = rec["dram_bytes_per_ray"] * (n_total / world)  # scaled to this launch's ray count
+                else:
+                    ncu_note = "profiles/ncu_summary.json was captured from different kernel sources (hash %s, now %s): ncu-derived fields withheld" % (
+                        rec.get("source_hash"), _build.source_hash())
             except Exception:
                 pass
+            sm_clock_hz = 1e6 * float((sampler.summary().get("sm_mhz") or 1965.0))
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            rays_rank = n_total / world
+            lane_issue_peak = n_sm * 4 * 32 * sm_clock_hz   # lane-instructions per second the SMs can issue
+            steps_per_ray = 0.5 * cnt["nodes_per_ray"]["total"]  # a node step = one internal node fetch + both child box tests
+            eff = {
+                "node_steps_per_s": steps_per_ray * rays_rank / (t_fwd_ms * 1e-3),
+                "node_steps_per_ray_canonical": steps_per_ray,
+                "q1_hit_frac": (stage_counts["entry_hits"] / max(1, n_local)) if stage_counts else cnt.get("q1_hit_frac"),
+                "valid_frac": (stage_counts["valid_paths"] / max(1, n_local)) if stage_counts else None,
+                "beam_tiles_kept_frac": (stage_counts["tiles_kept"] / stage_counts["tiles"]) if stage_counts and stage_counts.get("tiles") else None,
+                "rays_per_s_over_hit_rays": (stage_counts["entry_hits"] / (t_fwd_ms * 1e-3)) if stage_counts else None,
+                "lane_inst_per_ray": ncu.get("lane_inst_per_ray") if ncu else None,
+                "lanes_per_inst": ncu.get("lanes_per_inst") if ncu else None,
+                "issue_frac": (ncu["lane_inst_per_ray"] * rays_rank / (t_fwd_ms * 1e-3) / lane_issue_peak) if ncu and ncu.get("lane_inst_per_ray") else None,
+                "warp_issue_frac": (ncu["warp_inst_per_ray"] * rays_rank / (t_fwd_ms * 1e-3) / (n_sm * 4 * sm_clock_hz)) if ncu and ncu.get("warp_inst_per_ray") else None,
+                "ncu": ncu_note,
+                "note": "the query kernels are bound by divergent per-ray traversal (latency of dependent node fetches, issue slots), not by HBM: "
+                        "issue_frac = executed lane-instructions/s over 148 SM x 4 schedulers x 32 lanes x SM clock is the efficiency figure; "
+                        "`frac` is the no-cache HBM model of SURVEY.md 8(d), kept for continuity",
+            }
             roof = {"bound": "hbm", "kernel": ("forward wavefront = ls_q1+ls_r1+ls_q2+ls_r2+ls_q3 (first five launches of drt_ray_loss_step)" if args.loss_path == "step" else "fused forward = wf_q1+wf_r1+wf_q2+wf_r2+wf_q3 (one drt_trace_fwd call)"), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "dram_gbs_actual": (traffic / (t_fwd_ms * 1e-3) / 1e9) if traffic else None,
                     "peak_source": peak_src, "bytes_per_ray_fwd": b_fwd, "bytes_per_ray_total": b_tot,
                     "kernel_ms": t_fwd_ms, "rays_per_launch": n_total // world,
                     "step_frac": (b_tot * (n_total / world) / ((t_fwd_ms + t_bwd_ms) * 1e-3) / 1e9) / peak,
                     "model": "no-cache traversal bytes on the canonical LBVH (profiles/canonical_counters.json)"}
+            roof.update(eff)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -698,6 +750,11 @@ def run_b200(args):
                        "int_ior": configs.INT_IOR, "valid_frac_rank0": valid_frac},
             "phases_ms": {"bvh_build": t_build_ms, "fwd": t_fwd_ms, "loss_grad": phases[2], "bwd": t_bwd_ms, "allreduce": t_ar_ms},
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "e2e_vs_cpu_baseline": ({"compact_layout": e2e["value"] / cpu["value"] if e2e else None,
+                                     "reference_layout": (e2e_ref_layout or e2e)["value"] / cpu["value"] if (e2e_ref_layout or e2e) else None,
+                                     "note": "e2e (host buffers, copies timed) over the CPU port on this box's host cores; `e2e` is the loader's lossless compact "
+                                             "layout (26 B/ray), `e2e_reference_layout` the reference's dense per-view tensors (73 B/ray): quote both"}
+                                    if cpu and (e2e or e2e_ref_layout) else None),
             "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "e2e": e2e, "e2e_reference_layout": e2e_ref_layout, "e2e_pinhole": e2e_pinhole, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "loss": loss_val, "grad_norm": grad_norm,
             "stage_counts_rank0": stage_counts, "parity_check": parity, "allreduce_check": ar_check, "shard": {"policy": args.shard if world > 1 else "none", "skew": shard_skew},

@@ -188,6 +188,7 @@ class Scene:
     def _edges(self):
         if not self._edges_ready:  # DiffRender.py:338-355, built lazily (only vh_loss / sm_loss need it)
             self.Edges, self.E2F, self._mean_len = silhouette.build_edge_tables(self.mesh, self.faces, self._dev)
+            self._E2F32 = self.E2F.to(torch.int32).contiguous()   # what drt_silhouette_classify reads
             self._edges_ready = True
         return self.Edges, self.E2F
 
@@ -200,10 +201,9 @@ class Scene:
         _, E2F = self._edges()
         return silhouette.dihedral_cos(self.vertices, E2F)
 
-    def silhouette_edge(self, origin):  # DiffRender.py:445-457
-        Edges, E2F = self._edges()
-        return silhouette.silhouette_edges(self.vertices, Edges, E2F, origin)
+    def silhouette_edge(self, origin):  # DiffRender.py:445-457 -> drt_silhouette_classify
+        Edges, _ = self._edges()
+        return silhouette.silhouette_edges(self.vertices, Edges, self._E2F32, origin)
 
-    def primary_visibility(self, silhouette_edge, camera_M, origin, detach_depth=False):  # DiffRender.py:459-479
-        return silhouette.primary_visibility(self.vertices, silhouette_edge, camera_M, origin, self.optix_intersect, Ray,
-                                             resy, resx, detach_depth)
+    def primary_visibility(self, silhouette_edge, camera_M, origin, detach_depth=False):  # DiffRender.py:459-479 -> drt_silhouette_sample
+        return silhouette.primary_visibility(self.optix_mesh, self.vertices, silhouette_edge, camera_M, origin, resy, resx, detach_depth)

@@ -19,6 +19,18 @@ def sources():
         os.path.join(os.path.dirname(HERE), "include", "drt_b200.h")]
 
 
+def source_hash():
+    """sha1 over the kernel sources and the C header: profiles/ncu_summary.json records it, bench.py refuses ncu-derived
+    figures (roofline.traffic, lane statistics) that were captured from different kernels."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in sources():
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(os.path.basename(f).encode())
+            h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def needs_build():
     if not os.path.exists(SO):
         return True

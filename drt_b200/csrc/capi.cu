@@ -7,8 +7,10 @@
 #include <memory>
 
 #include "../../include/drt_b200.h"
+#include "bvh_coop.cuh"
 #include "loss_step.cuh"
 #include "peer_allreduce.cuh"
+#include "silhouette.cuh"
 
 using namespace drt;
 
@@ -64,6 +66,7 @@ struct Tuning {
     int r_grid = 8;       // DRT_R_GRID: blocks per SM of the dense refraction kernels' grids
     bool tile = true;  // DRT_TILE=0: keep scanline batches in drt_ray_loss_step even when the image size is known (A/B switch)
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
+    bool coop_build = false;  // DRT_COOP_BUILD=1: the LBVH build as ONE cooperative launch (bvh_coop.cuh) -- measured SLOWER on B200 (0.208 vs 0.170 ms at 50 k triangles: 15 grid-wide barriers at ~5 us each and L2-only reads cost more than 18 launch boundaries), kept as a tested option
     bool beam = true;  // DRT_BEAM=0: entry query without beam culling of whole pixel tiles (A/B switch)
     int beam_steps = 1 << 30;  // DRT_BEAM_STEPS: node steps after which an undecided beam is kept
     int beam_tpb = 0;  // DRT_BEAM_TPB = 1..32 forces the tiles a warp takes per work fetch (default: by batch size)
@@ -105,6 +108,8 @@ struct Tuning {
         if (pl && !strcmp(pl, "1")) prefer_l1 = true;
         const char* bm = getenv("DRT_BWD_MERGE");
         if (bm && (!strcmp(bm, "0") || !strcmp(bm, "1"))) bwd_merge = atoi(bm);
+        const char* cb = getenv("DRT_COOP_BUILD");
+        if (cb && !strcmp(cb, "1")) coop_build = true;
         const char* bm2 = getenv("DRT_BEAM");
         if (bm2 && !strcmp(bm2, "0")) beam = false;
         const char* bs = getenv("DRT_BEAM_STEPS");
@@ -154,6 +159,7 @@ struct drt_bvh {
     unsigned long long* last_ctl = nullptr;      // control block of the latest drt_ray_loss_step (drt_bvh_last_counts)
     int64_t last_tiles = 0;                      // its number of 32-ray tiles (0: no beam pass)
     int work_slot = 0;
+    int build_blocks_per_sm = 0;                 // co-resident blocks of lbvh_build_kernel (0: no cooperative launch)
     int fused_blocks_per_sm = 0;                 // co-resident blocks of wf_fused_kernel<8> (0: no cooperative launch)
     int fused6_blocks_per_sm = 0;                // same for the 80-register variant
     int img_w = 0, img_h = 0;                    // drt_bvh_set_image_size: rays of drt_trace_fwd are whole scanline images
@@ -234,9 +240,29 @@ __global__ void init_scene_kernel(unsigned* scene, bool reset_bad)
     else if (threadIdx.x == 6 && reset_bad) scene[6] = 0u;
 }
 
-int fit_and_emit(drt_bvh* b, cudaStream_t st)
+// the whole (re)build, or the refit, as ONE cooperative launch (bvh_coop.cuh); V64 != nullptr: cast the vertices first
+int coop_build(drt_bvh* b, const double* V64, int refit, cudaStream_t st)
 {
     const int n = b->nF;
+    BuildArgs a{b->F, b->V32, V64, b->nV, n, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris, refit};
+    const int64_t work = std::max<int64_t>(n, V64 ? 3 * (int64_t)b->nV : 0);
+    // a small grid keeps the grid-wide barriers short: one block per SM at most
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_for(work, kSortThreads), std::min(b->sm_count, b->sm_count * b->build_blocks_per_sm)));
+    void* args[] = {&a};
+    CU(cudaLaunchCooperativeKernel((void*)lbvh_build_kernel, dim3(grid), dim3(kSortThreads), args, 0, st));
+    ++g_launches;
+    b->sorted_keys = b->keys + n;
+    return DRT_OK;
+}
+
+int fit_and_emit(drt_bvh* b, cudaStream_t st, const double* pending_V64 = nullptr)
+{
+    const int n = b->nF;
+    if (n > 0 && DRT_QNODE && tuning().coop_build && b->build_blocks_per_sm > 0 && b->sorted_keys) return coop_build(b, pending_V64, 1, st);
+    if (pending_V64) {
+        cast_vertices_kernel<<<blocks_for(3 * (int64_t)b->nV, 256), 256, 0, st>>>(pending_V64, b->V32, 3 * b->nV);
+        ++g_launches;
+    }
     if (n <= 0) return DRT_OK;
     if (n > 1) CU(cudaMemsetAsync(b->flags, 0, sizeof(int) * (size_t)(n - 1), st));
     fit_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_keys, n, b->children, b->parent, b->blo, b->bhi,
@@ -248,12 +274,19 @@ int fit_and_emit(drt_bvh* b, cudaStream_t st)
     return DRT_OK;
 }
 
-int build_tree(drt_bvh* b, cudaStream_t st)
+// pending_V64: float64 vertices whose float32 cast (into b->V32) is still to be done -- folded into the cooperative kernel
+int build_tree(drt_bvh* b, cudaStream_t st, const double* pending_V64 = nullptr)
 {
     const int n = b->nF;
     b->built = true;
     b->builds++;
-    if (n <= 0) return DRT_OK;
+    if (n <= 0) {
+        if (pending_V64 && b->nV > 0) {
+            cast_vertices_kernel<<<blocks_for(3 * (int64_t)b->nV, 256), 256, 0, st>>>(pending_V64, b->V32, 3 * b->nV);
+            ++g_launches;
+        }
+        return DRT_OK;
+    }
     int rc;
     if ((rc = ensure(b->keys, b->capK, 2 * (size_t)n))) return rc;
     if ((rc = ensure(b->sort_table, b->capSt, 256 * (size_t)sort_tiles(n)))) return rc;
@@ -264,6 +297,11 @@ int build_tree(drt_bvh* b, cudaStream_t st)
     if ((rc = ensure(b->flags, b->capFl, (size_t)n))) return rc;
     if ((rc = ensure(b->nodes, b->capN, (size_t)kNodeQuads * (size_t)(n > 1 ? n - 1 : 1)))) return rc;
     if ((rc = ensure(b->tris, b->capT, (size_t)kTriD2 * (size_t)n))) return rc;
+    if (DRT_QNODE && tuning().coop_build && b->build_blocks_per_sm > 0) return coop_build(b, pending_V64, 0, st);
+    if (pending_V64) {
+        cast_vertices_kernel<<<blocks_for(3 * (int64_t)b->nV, 256), 256, 0, st>>>(pending_V64, b->V32, 3 * b->nV);
+        ++g_launches;
+    }
 
     init_scene_kernel<<<1, 32, 0, st>>>(b->scene, false); ++g_launches;
     centroid_bounds_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene); ++g_launches;
@@ -275,9 +313,10 @@ int build_tree(drt_bvh* b, cudaStream_t st)
         ++g_launches;
     }
     CU(cudaGetLastError());
-    return fit_and_emit(b, st);
+    return fit_and_emit(b, st);  // (the multi-launch path: vertices were cast above)
 }
 
+// float32 vertices are copied now; float64 ones are cast by whoever builds next (build_tree / fit_and_emit: pending_V64)
 int set_vertices(drt_bvh* b, const float* V32, const double* V64, int nV, cudaStream_t st)
 {
     int rc;
@@ -285,10 +324,7 @@ int set_vertices(drt_bvh* b, const float* V32, const double* V64, int nV, cudaSt
     b->nV = nV;
     if (nV <= 0) return DRT_OK;
     if (V32) CU(cudaMemcpyAsync(b->V32, V32, sizeof(float) * 3 * (size_t)nV, cudaMemcpyDeviceToDevice, st));
-    else {
-        cast_vertices_kernel<<<blocks_for(3 * (int64_t)nV, 256), 256, 0, st>>>(V64, b->V32, 3 * nV);
-        ++g_launches;
-    }
+    (void)V64;
     CU(cudaGetLastError());
     return DRT_OK;
 }
@@ -313,7 +349,7 @@ int build_common(drt_bvh* b, const int32_t* F, int nF, const float* V32, const d
         ++g_launches;
     }
     CU(cudaGetLastError());
-    return build_tree(b, st);
+    return build_tree(b, st, V32 ? nullptr : V64);
 }
 
 }  // namespace
@@ -359,6 +395,7 @@ int drt_bvh_create(int device, drt_bvh** out)
     {
         int coop = 0;
         CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        if (coop) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->build_blocks_per_sm, lbvh_build_kernel, kSortThreads, 0));
         if (coop) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->fused_blocks_per_sm, wf_fused_kernel<8>, 128, 0));
         if (coop) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->fused6_blocks_per_sm, wf_fused_kernel<6>, 128, 0));
     }
@@ -405,8 +442,8 @@ int drt_bvh_update_vert(drt_bvh* b, const float* V32, const double* V64, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if ((rc = set_vertices(b, V32, V64, nV, st))) return rc;
-    if (refit) { b->refits++; return fit_and_emit(b, st); }
-    return build_tree(b, st);
+    if (refit) { b->refits++; return fit_and_emit(b, st, V64); }
+    return build_tree(b, st, V64);
 }
 
 int drt_bvh_set_image_size(drt_bvh* b, int32_t image_w, int32_t image_h)
@@ -494,9 +531,9 @@ int drt_trace_fwd(drt_bvh* b, const double* V64, const double* origin, const dou
         int rc;
         if ((rc = ensure(b->listA, b->capLA, (size_t)N))) return rc;
         if ((rc = ensure(b->listB, b->capLB, (size_t)N))) return rc;
-        // per-launch control block: 3 work counters (Q1,Q2,Q3) + countL + countM
-        unsigned long long* ctl = b->work + (size_t)(b->work_slot++ % (kWorkSlots / 4)) * 4;
-        CU(cudaMemsetAsync(ctl, 0, 4 * sizeof(unsigned long long), st));
+        // per-launch control block: 3 work counters (Q1,Q2,Q3) + {countL, countM} + - + {tiles kept} + tile-list work counter
+        unsigned long long* ctl = b->work + (size_t)(b->work_slot++ % (kWorkSlots / 8)) * 8;
+        CU(cudaMemsetAsync(ctl, 0, 8 * sizeof(unsigned long long), st));
         int* countL = (int*)(ctl + 3);
         int* countM = countL + 1;
         const int* pol = tuning().pol;
@@ -529,6 +566,17 @@ int drt_trace_fwd(drt_bvh* b, const double* V64, const double* origin, const dou
         else if (minb == 6) KERNEL<6><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
         else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
     } while (0)
+#if DRT_QNODE
+        if (tuning().beam && (pol[0] & 0xff) == 32) {
+            // beam pass over all 32-ray tiles (culled tiles are zero-filled), then the per-ray entry query over the survivors;
+            // the tile list lives in listB, which is free until R2
+            int2* tiles = reinterpret_cast<int2*>(b->listB);
+            int* n_tiles = (int*)(ctl + 5);
+            wf_beam_kernel<<<pg, 128, 0, st>>>(b->view(), j1, (int)N, ctl + 0, beam_tiles_per_fetch(N, pg * 4), tuning().beam_steps, tiles, n_tiles);
+            ++g_launches;
+            DRT_LAUNCH_Q(wf_q1_tiles_kernel, b->view(), j1, (int)N, tiles, n_tiles, ctl + 6, pol[0]);
+        } else
+#endif
         DRT_LAUNCH_Q(wf_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
         wf_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, origin, dir, ext_ior, int_ior, out_ori, out_dir, mask3, b->listA, countL);
         ExitJob j2{out_ori, out_dir, b->listA};
@@ -709,6 +757,62 @@ int drt_generate_rays(int32_t resy, int32_t resx, const double* K_inverse, const
     const int64_t n = (int64_t)resy * resx;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_for(n, 256), (int64_t)sms * 16));
     generate_rays_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(resy, resx, K_inverse, R_inverse, origin3, dir); ++g_launches;
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+// ---- silhouette-edge sampling -----------------------------------------------------------------------
+int drt_silhouette_classify(const double* V64, const int32_t* e2f, int64_t nE, const double* origin3, uint8_t* flags, void* stream)
+{
+    if (nE < 0) return fail(DRT_ERR_INVALID, "drt_silhouette_classify: nE < 0");
+    if (nE == 0) return DRT_OK;
+    if (!V64 || !e2f || !origin3 || !flags) return fail(DRT_ERR_INVALID, "drt_silhouette_classify: null buffer");
+    int dev = 0, sms = 148;
+    CU(device_of(flags, &dev));
+    DeviceGuard g(dev);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<int64_t>(blocks_for(nE, 256), (int64_t)sms * 8);
+    silhouette_classify_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(V64, e2f, nE, origin3, flags); ++g_launches;
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_silhouette_sample(const drt_bvh* b, const double* V64, const int64_t* edges, int64_t k, const double* R, const double* K,
+                          const double* R_inverse, const double* K_inverse, const double* origin3, int32_t resx, int32_t resy,
+                          int64_t* index_xy, double* f, uint8_t* keep, void* stream)
+{
+    if (!b) return fail(DRT_ERR_INVALID, "drt_silhouette_sample: null handle");
+    if (!b->built) return fail(DRT_ERR_STATE, "drt_silhouette_sample: no mesh has been set (update_mesh first)");
+    if (k < 0) return fail(DRT_ERR_INVALID, "drt_silhouette_sample: k < 0");
+    if (k == 0) return DRT_OK;
+    if (!V64 || !edges || !R || !K || !R_inverse || !K_inverse || !origin3 || !index_xy || !f || !keep)
+        return fail(DRT_ERR_INVALID, "drt_silhouette_sample: null buffer");
+    DeviceGuard g(b->device);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", b->device);
+    const int grid = (int)std::min<int64_t>(blocks_for(2 * k, 128), (int64_t)b->sm_count * 8);
+    silhouette_sample_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, edges, k, Camera{R, K, R_inverse, K_inverse}, origin3, resx,
+                                                                     resy, index_xy, f, keep);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_silhouette_backward(const double* V64, const int64_t* edges, const double* R, const double* K, int detach_depth, const double* f,
+                            const int64_t* kept_idx, const float* g_output, int64_t m, double* grad_V, void* stream)
+{
+    if (m < 0) return fail(DRT_ERR_INVALID, "drt_silhouette_backward: m < 0");
+    if (m == 0) return DRT_OK;
+    if (!V64 || !edges || !R || !K || !f || !kept_idx || !g_output || !grad_V) return fail(DRT_ERR_INVALID, "drt_silhouette_backward: null buffer");
+    int dev = 0, sms = 148;
+    CU(device_of(grad_V, &dev));
+    DeviceGuard g(dev);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<int64_t>(blocks_for(m, 128), (int64_t)sms * 8);
+    silhouette_backward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(V64, edges, Camera{R, K, nullptr, nullptr}, detach_depth, f, kept_idx,
+                                                                       g_output, m, grad_V);
+    ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
 }

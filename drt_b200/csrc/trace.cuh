@@ -120,6 +120,18 @@ typedef SharedStack QueryStack;
 typedef LocalStack QueryStack;
 #endif
 
+// DRT_FOLD_E: the slack of the box test (relative 2^-20 on tfar + E) folded into the far-plane addends;
+// DRT_FAR_SEL: far-plane selectors precomputed; DRT_LDG256: one 256-bit node load (LDG.E.256, sm_100a) instead of two 128-bit ones.
+#ifndef DRT_FOLD_E
+#define DRT_FOLD_E 0
+#endif
+#ifndef DRT_FAR_SEL
+#define DRT_FAR_SEL 0
+#endif
+#ifndef DRT_LDG256
+#define DRT_LDG256 0
+#endif
+
 struct RayQ {
     QRay r;
     float ix, iy, iz;  // 1/d            (quantised nodes: A = s/d, the grid step over the direction)
@@ -127,6 +139,12 @@ struct RayQ {
     float E;           // additive slack, 0 for origins within 64*pmax (quantised: within 64 extents of the grid)
 #if DRT_QNODE
     unsigned sx, sy, sz;  // PRMT selector of the NEAR plane of a (lo | hi << 16) pair on each axis
+#if DRT_FOLD_E
+    float fcx, fcy, fcz;  // addends of the FAR planes: C' + slack (see ray_setup), so that a box test is just near <= far
+#endif
+#if DRT_FAR_SEL
+    unsigned fsx, fsy, fsz;  // selectors of the FAR planes, kept in registers (else s ^ 0x22 in every node step)
+#endif
 #endif
 };
 
@@ -171,7 +189,32 @@ __device__ __forceinline__ RayQ ray_setup(const BvhView& B, const QRay& r)
     const float k = 64.f * 65520.f;
     if (!(fabsf(wx) <= k * sx && fabsf(wy) <= k * sy && fabsf(wz) <= k * sz))
         q.E = 4.76837158203125e-07f * fmaxf(fabsf(cx) + fabsf(mx), fmaxf(fabsf(cy) + fabsf(my), fabsf(cz) + fabsf(mz)));
+#if DRT_FOLD_E
+    // Far planes carry their slack in the addend: per axis 2^-21 (|C| + 65536 |A|) >= 4 x the rounding of any plane distance
+    // on that axis (|t| <= |C| + 65536 |A| inside the grid; the FMA rounds the RESULT once, 2^-24 |t|, on the near and on the
+    // far side), plus the far-origin slack E.  The sum is rounded UP, so folding only ever widens a box; the rounding of the
+    // folded addend itself (<= 0.5 grid step, upward) stays inside the 3 steps of outward margin of the stored planes.
+    q.fcx = __fadd_ru(q.cx, fmaf(4.76837158203125e-07f, fabsf(cx) + 65536.f * fabsf(q.ix), q.E));
+    q.fcy = __fadd_ru(q.cy, fmaf(4.76837158203125e-07f, fabsf(cy) + 65536.f * fabsf(q.iy), q.E));
+    q.fcz = __fadd_ru(q.cz, fmaf(4.76837158203125e-07f, fabsf(cz) + 65536.f * fabsf(q.iz), q.E));
+#endif
+#if DRT_FAR_SEL
+    asm volatile("xor.b32 %0, %1, 0x22;" : "=r"(q.fsx) : "r"(q.sx));  // opaque: not rematerialised inside the loop
+    asm volatile("xor.b32 %0, %1, 0x22;" : "=r"(q.fsy) : "r"(q.sy));
+    asm volatile("xor.b32 %0, %1, 0x22;" : "=r"(q.fsz) : "r"(q.sz));
+#endif
     return q;
+}
+
+// closest-hit bound as the box test uses it: with the folded slack the test is near <= min(far planes, tmax), so the
+// bound itself carries the slack (a tie at exactly t_best in another box must still pass)
+__device__ __forceinline__ float tmax_of(const RayQ& q, double t)
+{
+#if DRT_QNODE && DRT_FOLD_E
+    return fmaf(__double2float_ru(t), 1.00000095367431640625f, q.E);
+#else
+    return __double2float_ru(t);
+#endif
 }
 
 // raw prmt.b32: __byte_perm would first mask the selector with 0x7777 (one more ALU op per axis and step)
@@ -209,21 +252,40 @@ template <class S>
 __device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float tmax, int node, S& stack, int& sp)
 {
     const uint4* p = B.nodes + (size_t)node * kNodeQuads;
+#if DRT_LDG256
+    uint4 a, b;
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+#else
     const uint4 a = __ldg(p), b = __ldg(p + 1);
+#endif
+#if DRT_FAR_SEL
+    const unsigned fx = q.fsx, fy = q.fsy, fz = q.fsz;
+#else
     const unsigned fx = q.sx ^ 0x22u, fy = q.sy ^ 0x22u, fz = q.sz ^ 0x22u;  // selectors of the FAR planes
-    const float2 Axy = make_float2(q.ix, q.iy), Cxy = make_float2(q.cx, q.cy), Azz = make_float2(q.iz, q.iz), Czz = make_float2(q.cz, q.cz);
+#endif
+    const float2 Axy = make_float2(q.ix, q.iy), Cxy = make_float2(q.cx, q.cy), Azz = make_float2(q.iz, q.iz);
+#if DRT_FOLD_E
+    const float2 Fxy = make_float2(q.fcx, q.fcy), Czz = make_float2(q.cz, q.fcz);
+#else
+    const float2 Fxy = Cxy, Czz = make_float2(q.cz, q.cz);
+#endif
     const float2 n0 = fma2(make_float2(qplane(a.x, q.sx), qplane(a.z, q.sy)), Axy, Cxy);
-    const float2 f0 = fma2(make_float2(qplane(a.x, fx), qplane(a.z, fy)), Axy, Cxy);
+    const float2 f0 = fma2(make_float2(qplane(a.x, fx), qplane(a.z, fy)), Axy, Fxy);
     const float2 n1 = fma2(make_float2(qplane(a.y, q.sx), qplane(a.w, q.sy)), Axy, Cxy);
-    const float2 f1 = fma2(make_float2(qplane(a.y, fx), qplane(a.w, fy)), Axy, Cxy);
+    const float2 f1 = fma2(make_float2(qplane(a.y, fx), qplane(a.w, fy)), Axy, Fxy);
     const float2 z0 = fma2(make_float2(qplane(b.x, q.sz), qplane(b.x, fz)), Azz, Czz);  // (near, far) of child 0 on z
     const float2 z1 = fma2(make_float2(qplane(b.y, q.sz), qplane(b.y, fz)), Azz, Czz);
     const float N0 = fmaxf(fmaxf(n0.x, n0.y), fmaxf(z0.x, 0.f));
     const float F0 = fminf(fminf(f0.x, f0.y), fminf(z0.y, tmax));
     const float N1 = fmaxf(fmaxf(n1.x, n1.y), fmaxf(z1.x, 0.f));
     const float F1 = fminf(fminf(f1.x, f1.y), fminf(z1.y, tmax));
+#if DRT_FOLD_E
+    const bool h0 = N0 <= F0, h1 = N1 <= F1;
+#else
     const bool h0 = N0 <= fmaf(F0, 1.00000095367431640625f, q.E);
     const bool h1 = N1 <= fmaf(F1, 1.00000095367431640625f, q.E);
+#endif
     const int c0 = (int)b.z, c1 = (int)b.w;
     if (h0 && h1) {
         const bool first0 = N0 <= N1;
@@ -394,8 +456,9 @@ __device__ __forceinline__ float warp_max_f32(float v)
 #endif  // DRT_QNODE
 
 // exact test of the one triangle of a leaf; updates the closest hit (ties -> lowest id)
-__device__ __forceinline__ bool leaf_step(const BvhView& B, const QRay& r, int leaf, double& t_best, int& id_best, float& tmax)
+__device__ __forceinline__ bool leaf_step(const BvhView& B, const RayQ& q, int leaf, double& t_best, int& id_best, float& tmax)
 {
+    const QRay& r = q.r;
     const double2* p = B.tris + (size_t)(~leaf) * kTriD2;
     const double2 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
     double t;
@@ -406,7 +469,7 @@ __device__ __forceinline__ bool leaf_step(const BvhView& B, const QRay& r, int l
     if (t < t_best || (t == t_best && id < id_best)) {
         t_best = t;
         id_best = id;
-        tmax = __double2float_ru(t);
+        tmax = tmax_of(q, t);
     }
     return true;
 }
@@ -487,11 +550,11 @@ __device__ __forceinline__ void walk_vote(const BvhView& B, const RayQ& q, float
 
 // test the queued leaves; returns true as soon as ANY is satisfied
 template <bool ANY, class S>
-__device__ __forceinline__ bool drain(const BvhView& B, const QRay& r, S& stack, int& nd, double& t_best, int& id_best, float& tmax)
+__device__ __forceinline__ bool drain(const BvhView& B, const RayQ& q, S& stack, int& nd, double& t_best, int& id_best, float& tmax)
 {
     while (nd > 0) {
         --nd;
-        bool hit = leaf_step(B, r, stack.leaf_get(nd), t_best, id_best, tmax);
+        bool hit = leaf_step(B, q, stack.leaf_get(nd), t_best, id_best, tmax);
         if (ANY && hit) { nd = 0; return true; }
     }
     return false;
@@ -513,7 +576,7 @@ __device__ __forceinline__ void traverse(const BvhView& B, const QRay& r, double
     int node = 0;
     for (;;) {
         walk(B, q, tmax, node, stack, sp, nd);
-        if (drain<ANY>(B, r, stack, nd, t_best, id_best, tmax)) return;
+        if (drain<ANY>(B, q, stack, nd, t_best, id_best, tmax)) return;
         if (node == kDone) return;
     }
 }

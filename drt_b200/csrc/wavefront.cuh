@@ -98,7 +98,7 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
         for (;;) {
             if (vote) walk_vote(B, q, tmax, node, stack, sp, nd, vote);
             else walk(B, q, tmax, node, stack, sp, nd);
-            if (drain<ANY>(B, q.r, stack, nd, t_best, id_best, tmax)) { node = kDone; stack.reset(sp); }
+            if (drain<ANY>(B, q, stack, nd, t_best, id_best, tmax)) { node = kDone; stack.reset(sp); }
             unsigned fin = __ballot_sync(FULL, item >= 0 && node == kDone);
             if (__popc(fin) >= need) break;
         }
@@ -218,7 +218,7 @@ __device__ __forceinline__ void entry_query_tiles(const BvhView& B, Job& job, in
         for (;;) {
             if (vote) walk_vote(B, q, tmax, node, stack, sp, nd, vote);
             else walk(B, q, tmax, node, stack, sp, nd);
-            drain<false>(B, q.r, stack, nd, t_best, id_best, tmax);
+            drain<false>(B, q, stack, nd, t_best, id_best, tmax);
             if (!__any_sync(FULL, node != kDone)) break;
         }
         if (act) job.retire(item, id_best, t_best);
@@ -305,6 +305,27 @@ __global__ void __launch_bounds__(128, MINB) wf_q1_kernel(BvhView B, EntryJob jo
     DRT_QUERY_STACK(stack);
     persistent_query<false>(B, job, N, work, policy, stack);
 }
+
+#if DRT_QNODE
+// the same entry query with beam culling (beam_pass / entry_query_tiles above): culled tiles are zero-filled by retire()
+__global__ void __launch_bounds__(128, 8) wf_beam_kernel(BvhView B, EntryJob job, int N, unsigned long long* work, int tpb, int max_steps,
+                                                         int2* __restrict__ tiles, int* __restrict__ n_tiles)
+{
+    job.zeros = nullptr;
+    job.issued = false;
+    beam_pass(B, job, N, work, tpb, max_steps, tiles, n_tiles);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) wf_q1_tiles_kernel(BvhView B, EntryJob job, int N, const int2* __restrict__ tiles,
+                                                                const int* __restrict__ n_tiles, unsigned long long* work, int policy)
+{
+    job.zeros = nullptr;
+    job.issued = false;
+    DRT_QUERY_STACK(stack);
+    entry_query_tiles(B, job, N, tiles, n_tiles, work, policy, stack);
+}
+#endif
 
 // ---- R1: refraction at the entry hit, dense over L ------------------------------------------------
 __device__ __forceinline__ void r1_body(const BvhView& B, const double* __restrict__ V64,

@@ -1,9 +1,10 @@
-"""Silhouette-edge visibility sampling on top of the closest-hit query.
+"""Silhouette-edge visibility sampling on the fused kernels of csrc/silhouette.cuh.
 
-Same quantities as the reference's edge machinery -- init_edge (DiffRender.py:338-355), edge_face_norm
-(:150-163), silhouette_edge (:445-457), primary_visibility (:459-479), primary_edge_sample (:189-267),
-dihedral_angle (:440-443) -- written against drt_b200.trimesh_lite and Scene.optix_intersect, i.e. the
-two rays per silhouette edge go through drt_closest_hit (un-normalised directions are fine there).
+Same quantities as the reference's edge machinery -- init_edge (DiffRender.py:338-355), edge_face_norm (:150-163),
+silhouette_edge (:445-457), primary_visibility (:459-479), primary_edge_sample (:189-267), dihedral_angle (:440-443).
+Edge classification is one kernel over the E2F table; projection + the two probe rays per silhouette edge + the in-image
+filter are one kernel that walks the BVH itself; the backward is one kernel.  (A PyTorch restatement of the same functions,
+used by the CPU tests, lives in oracle/silhouette_torch.py.)
 """
 import numpy as np
 import torch
@@ -43,67 +44,73 @@ def dihedral_cos(vertices, E2F):
     return (n1 * n2).sum(dim=1)
 
 
-def silhouette_edges(vertices, Edges, E2F, origin):
-    """Edges whose two faces face opposite ways as seen from `origin` (DiffRender.py:445-457)."""
-    assert origin.dim() == 1
-    v = vertices.detach()
-    n1, n2 = edge_face_norm(v, E2F)
-    d1 = (n1 * (origin - v[E2F[:, 0, 0]])).sum(dim=1)
-    d2 = (n2 * (origin - v[E2F[:, 1, 0]])).sum(dim=1)
-    return Edges[torch.logical_xor(d1 > 0, d2 > 0)]
+def silhouette_edges(vertices, Edges, E2F32, origin):
+    """Scene.silhouette_edge (DiffRender.py:445-457) on drt_silhouette_classify: edges whose two faces face opposite ways as
+    seen from `origin`, in ascending edge order like the reference's boolean-mask index."""
+    import ctypes as C
+
+    from . import _lib, optix
+    if origin.dim() != 1 or origin.shape[0] != 3:
+        raise ValueError("origin must be a [3] tensor (DiffRender.py:446)")
+    V = vertices.detach().contiguous()
+    dev = V.device
+    optix.check_on(dev, Edges=Edges, E2F=E2F32, origin=origin)
+    if V.dtype != torch.float64 or E2F32.dtype != torch.int32:
+        raise TypeError("silhouette_edges works on float64 vertices and the int32 E2F table")
+    o = origin.detach().to(torch.float64).contiguous()
+    n_e = E2F32.shape[0]
+    flags = torch.empty(n_e, dtype=torch.bool, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("drt_silhouette_classify", optix._ptr(V), optix._ptr(E2F32), n_e, optix._ptr(o), optix._ptr(flags), optix._stream_ptr(dev))
+    return Edges[flags]
 
 
-class EdgeSample(torch.autograd.Function):
-    """One sample per silhouette edge: the edge midpoint in pixels; two probe rays one pixel either
-    side of the edge decide which side is covered.  Hand-written backward (DiffRender.py:189-267)."""
+class EdgeVisibility(torch.autograd.Function):
+    """Scene.primary_visibility + primary_edge_sample (DiffRender.py:459-479, 189-267) as two kernels: forward
+    drt_silhouette_sample (projection, midpoint sample, the two probe rays through the BVH, in-image filter), backward
+    drt_silhouette_backward (the reference's hand-written dE_pos chained through the projection into the vertices)."""
 
     @staticmethod
-    def forward(ctx, E_pos, intersect_fn, camera_M, ray_origin, ray_cls):
-        assert ray_origin.dim() == 1
-        n = E_pos.shape[0]
-        _, _, R_inv, K_inv = camera_M
-        a, b = E_pos[:, 0], E_pos[:, 1]                      # [n,2] pixel positions of the edge ends
-        mid = 0.5 * (a + b)
-        nrm = torch.stack((a[:, 1] - b[:, 1], b[:, 0] - a[:, 0]), dim=1)   # edge normal in the image
-        unit = nrm / nrm.norm(dim=1, keepdim=True)
-        probes = torch.cat((mid + unit, mid - unit), dim=0)  # [2n,2]: upper side then lower side
-        ones = torch.ones((2 * n, 1), dtype=E_pos.dtype, device=E_pos.device)
-        cam = torch.cat((probes, ones), dim=1) @ K_inv.T     # pixel at z = 1
-        world = torch.cat((cam, ones), dim=1) @ R_inv.T
-        direction = world[:, :3] - ray_origin.view(1, 3)     # NOT normalised, like the reference (:222)
-        _, hit = intersect_fn(ray_cls(ray_origin.view(1, 3).expand_as(direction), direction))
-        cover = hit.to(E_pos.dtype)
-        f = cover[:n] - cover[n:]
-        # dE[i, endpoint, coord] = -nrm[i, coord]  (DiffRender.py:243-249)
-        dE = torch.stack((torch.stack((-nrm[:, 0], -nrm[:, 0]), dim=1), torch.stack((-nrm[:, 1], -nrm[:, 1]), dim=1)), dim=2)
-        dE = dE * f.view(-1, 1, 1)
-        valid = f.abs() > 1e-5
-        index = mid[valid].to(torch.long)
-        output = 0.5 * torch.ones(index.shape[0], dtype=torch.float32, device=E_pos.device)
+    def forward(ctx, vertices, mesh, sil_edges, camera_M, origin, resy, resx, detach_depth):
+        from . import _lib, optix
+        dev = mesh.device
+        R, K, R_inv, K_inv = (m.detach().to(torch.float64).contiguous() for m in camera_M)
+        V = vertices.detach().contiguous()
+        E = sil_edges.contiguous()
+        o = origin.detach().to(torch.float64).contiguous()
+        optix.check_on(dev, vertices=V, silhouette_edge=E, R=R, K=K, R_inverse=R_inv, K_inverse=K_inv, origin=o)
+        if V.dtype != torch.float64 or E.dtype != torch.long or E.dim() != 2 or E.shape[1] != 2:
+            raise TypeError("primary_visibility needs float64 vertices and silhouette_edge long [k,2]")
+        if R.shape != (4, 4) or K.shape != (3, 3) or R_inv.shape != (4, 4) or K_inv.shape != (3, 3) or o.shape != (3,):
+            raise ValueError("camera_M must be (R [4,4], K [3,3], R_inverse [4,4], K_inverse [3,3]) and origin [3]")
+        k = E.shape[0]
+        index_xy = torch.empty((k, 2), dtype=torch.long, device=dev)
+        f = torch.empty(k, dtype=torch.float64, device=dev)
+        keep = torch.empty(k, dtype=torch.bool, device=dev)
+        _lib.call("drt_silhouette_sample", mesh._h, optix._ptr(V), optix._ptr(E), k, optix._ptr(R), optix._ptr(K), optix._ptr(R_inv),
+                  optix._ptr(K_inv), optix._ptr(o), int(resx), int(resy), optix._ptr(index_xy), optix._ptr(f), optix._ptr(keep),
+                  optix._stream_ptr(dev))
+        kept = torch.nonzero(keep, as_tuple=False).reshape(-1)     # ascending edge slot: the order of the reference's mask index
+        index = index_xy[kept]
+        output = torch.full((kept.shape[0],), 0.5, dtype=torch.float32, device=dev)   # DiffRender.py:240
+        ctx.save_for_backward(V, E, R, K, f, kept)
+        ctx.detach_depth = bool(detach_depth)
         ctx.mark_non_differentiable(index)
-        ctx.save_for_backward(dE, valid)
         return index, output
 
     @staticmethod
     def backward(ctx, _g_index, g_output):
-        dE, valid = ctx.saved_tensors
-        g = dE.clone()
-        g[valid] = g[valid] * g_output.view(-1, 1, 1).to(g.dtype)
-        return g, None, None, None, None
+        from . import _lib, optix
+        V, E, R, K, f, kept = ctx.saved_tensors
+        grad_V = torch.zeros_like(V)
+        if g_output is not None and kept.shape[0]:
+            g = g_output.detach().to(torch.float32).contiguous()
+            with torch.cuda.device(V.device):
+                _lib.call("drt_silhouette_backward", optix._ptr(V), optix._ptr(E), optix._ptr(R), optix._ptr(K), int(ctx.detach_depth),
+                          optix._ptr(f), optix._ptr(kept), optix._ptr(g), kept.shape[0], optix._ptr(grad_V), optix._stream_ptr(V.device))
+        return grad_V, None, None, None, None, None, None, None
 
 
-def primary_visibility(vertices, silhouette_edge, camera_M, origin, intersect_fn, ray_cls, resy, resx, detach_depth=False):
-    """Project the silhouette edges, sample them, drop samples outside the image (DiffRender.py:459-479).
-    -> (index long[m,2] pixel (x,y), output float[m])."""
-    R, K, _, _ = camera_M
-    V = vertices[silhouette_edge.reshape(-1)]
-    ones = torch.ones((V.shape[0], 1), dtype=V.dtype, device=V.device)
-    cam = R @ torch.cat((V, ones), dim=1).T                   # [4,2n]
-    xyz = cam[:3]
-    if detach_depth:
-        xyz = torch.cat((xyz[:2], xyz[2:3].detach()), dim=0)
-    pix = K @ xyz
-    E_pos = (pix[:2] / pix[2]).T.reshape(-1, 2, 2)
-    index, output = EdgeSample.apply(E_pos, intersect_fn, camera_M, origin, ray_cls)
-    keep = (index[:, 0] < resx - 1) & (index[:, 1] < resy - 1) & (index[:, 0] >= 0) & (index[:, 1] >= 0)
-    return index[keep], output[keep]
+def primary_visibility(mesh, vertices, silhouette_edge, camera_M, origin, resy, resx, detach_depth=False):
+    """-> (index long[m,2] pixel (x,y) of the kept samples, output float32[m] = 0.5 with the reference's gradient)."""
+    return EdgeVisibility.apply(vertices, mesh, silhouette_edge, camera_M, origin, resy, resx, detach_depth)

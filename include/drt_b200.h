@@ -202,6 +202,35 @@ DRT_API int drt_generate_rays(int32_t resy, int32_t resx, const double* K_invers
                       double* dir, void* stream);
 
 /*
+ * Silhouette-edge sampling, the second consumer of the plugin (optim.py:67-80 calls it for 8 views per
+ * iteration).  All pointers are device pointers; float64 like the reference.
+ *
+ * drt_silhouette_classify replaces Scene.silhouette_edge -- DiffRender.py:445-457 (+ edge_face_norm :150-163):
+ *   e2f int32[nE,2,3] = the vertex triples of the two faces on every edge (Scene.E2F, DiffRender.py:352-355), origin3 = the
+ *   camera centre; flags[e] = 1 iff the two faces face opposite ways as seen from the origin (the reference's
+ *   logical_xor(dot1 > 0, dot2 > 0)); the caller compacts Edges[flags] (order-preserving, as the reference's mask index does).
+ *
+ * drt_silhouette_sample replaces Scene.primary_visibility + primary_edge_sample.forward -- DiffRender.py:459-479, 189-241:
+ *   for each of the k silhouette edges (edges int64[k,2] vertex ids): both ends projected with R float64[4,4] and
+ *   K float64[3,3] (row-major), the midpoint sample, the image-space edge normal, the two probe rays one pixel either side
+ *   (through K_inverse / R_inverse, un-normalised directions, float32 query like Scene.optix_intersect :386-392),
+ *   index_xy int64[k,2] = the sample truncated to a pixel, f float64[k] = cover(upper) - cover(lower),
+ *   keep uint8[k] = |f| > 1e-5 and 0 <= x < resx-1 and 0 <= y < resy-1 (:236, :476).  The handle is only read.
+ *
+ * drt_silhouette_backward replaces primary_edge_sample.backward (:243-267) chained through the projection (:465-472):
+ *   kept_idx int64[m] = the edge slots whose samples were kept, g_output float32[m] = d loss / d output; accumulates
+ *   d loss / d vertices into grad_V float64[nV,3] (caller zeroes).  detach_depth as in primary_visibility (:468-469).
+ */
+DRT_API int drt_silhouette_classify(const double* V64, const int32_t* e2f, int64_t nE, const double* origin3, uint8_t* flags,
+                            void* stream);
+DRT_API int drt_silhouette_sample(const drt_bvh* bvh, const double* V64, const int64_t* edges, int64_t k, const double* R,
+                          const double* K, const double* R_inverse, const double* K_inverse, const double* origin3,
+                          int32_t resx, int32_t resy, int64_t* index_xy, double* f, uint8_t* keep, void* stream);
+DRT_API int drt_silhouette_backward(const double* V64, const int64_t* edges, const double* R, const double* K, int detach_depth,
+                            const double* f, const int64_t* kept_idx, const float* g_output, int64_t m, double* grad_V,
+                            void* stream);
+
+/*
  * The one collective of the path -- SURVEY.md 8(e): views are sharded over the GPUs of one box, the mesh and
  * BVH are replicated, grad_V float64[nV,3] is summed once per step (the reference itself is single-GPU,
  * optix_extend.cpp:10, so there is no reference interface to mirror).  One-shot all-reduce over NVLink /

@@ -111,3 +111,18 @@ def test_single_and_two_triangle_meshes_and_empty_slots(cuda_device):
     _check(cuda_device, v, np.array([[0, 1, 2]]), ray, 0.02)
     _check(cuda_device, v, np.array([[0, 1, 2], [1, 3, 2]]), ray, 0.05)
     _check(cuda_device, v, np.array([[0, 1, 2], [1, 3, 2], [0, 1, 3]]), ray, 0.05)
+
+
+def test_cooperative_build_and_no_beam_give_the_same_answers(cuda_device):
+    """The defaults are the 19-launch LBVH build and the beam-culled entry query; the parity suite must also hold with the
+    single cooperative build kernel and without beam culling -- run in a subprocess, the switches are read once."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DRT_COOP_BUILD="1", DRT_BEAM="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        os.path.join(root, "tests", "test_gpu_parity.py"), os.path.join(root, "tests", "test_gpu_loss_step.py"),
+                        "-k", "closest_hit or refit or loss_step_vs_oracle or edge_cases"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

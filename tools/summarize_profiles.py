@@ -12,6 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 launches = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "launches.csv")
 rep = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "prof_step.ncu-rep")
+RAYS = int(os.environ.get("PROFILE_RAYS", 5529600))  # rays per launch of the --set full capture (8 views 960x720)
+sys.path.insert(0, ROOT)
+from drt_b200 import build as _build  # noqa: E402
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
@@ -63,7 +66,21 @@ if os.path.exists(rep):
         ("launch__registers_per_thread", "registers"), ("smsp__inst_executed.sum", "warp instructions"),
         ("smsp__thread_inst_executed_per_inst_executed.ratio", "active lanes / instruction"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
-        ("launch__grid_size", "grid"), ("launch__block_size", "block")])
+        ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+        ("smsp__thread_inst_executed.sum", "lane instructions"),
+        ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe % of peak"),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe % of peak"),
+        ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe % of peak"),
+        ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 data-pipe wavefronts % of peak"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall: long scoreboard / issue"),
+        ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall: short scoreboard / issue"),
+        ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall: fixed-latency wait / issue"),
+        ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall: math pipe throttle / issue"),
+        ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall: not selected / issue"),
+        ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall: branch resolving / issue"),
+        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall: barrier / issue"),
+        ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall: LG throttle / issue"),
+        ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall: no instruction / issue")])
     summ = {}
     with open(os.path.join(out_dir, f"{tag}_ncu_full.md"), "w") as f:
         f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` of one bench step\n"
@@ -82,19 +99,36 @@ if os.path.exists(rep):
             def to_bytes(v, u):
                 v = float(v.replace(",", ""))
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            def num(k):
+                try:
+                    return float(d[k][0].replace(",", ""))
+                except Exception:
+                    return None
             if "dram__bytes_read.sum" in d:
-                summ[name] = {"dram_bytes_per_launch": to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"]),
-                              "duration": " ".join(d["gpu__time_duration.sum"]), "rays_per_launch": 5529600}
+                e = summ.setdefault(name, {"launches": 0, "dram_bytes_per_launch": 0.0, "warp_inst": 0.0, "lane_inst": 0.0, "duration_us": 0.0,
+                                           "rays_per_launch": RAYS})
+                e["launches"] += 1
+                e["dram_bytes_per_launch"] += to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])
+                e["warp_inst"] += num("smsp__inst_executed.sum") or 0.0
+                e["lane_inst"] += (num("smsp__thread_inst_executed.sum") or
+                                   (num("smsp__inst_executed.sum") or 0.0) * (num("smsp__thread_inst_executed_per_inst_executed.ratio") or 0.0))
+                dur, du = d["gpu__time_duration.sum"]
+                e["duration_us"] += float(dur.replace(",", "")) * {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}.get(du, 1.0)
+                e["issue_active_pct"] = num("smsp__issue_active.avg.pct_of_peak_sustained_active")
     js = os.path.join(out_dir, "ncu_summary.json")
     allj = json.load(open(js)) if os.path.exists(js) else {}
     allj[tag] = summ
     # bench.py reads the forward group: sum of the five wavefront launches, scaled per ray
     fwd = [v for k, v in summ.items() if k.startswith("wf_")]
     if fwd:
-        allj["trace_fwd"] = {"dram_bytes_per_ray": sum(v["dram_bytes_per_launch"] for v in fwd) / 5529600, "from": tag}
-    # the same five stages inside drt_ray_loss_step (ls_q1/r1/q2/r2/q3; ls_loss_bwd is the backward)
+        allj["trace_fwd"] = {"dram_bytes_per_ray": sum(v["dram_bytes_per_launch"] for v in fwd) / RAYS, "from": tag, "source_hash": _build.source_hash()}
+    # the forward stages inside drt_ray_loss_step (ls_beam/q1_tiles/r1/q2/r2/q3; ls_loss_bwd is the backward)
     ls = [v for k, v in summ.items() if k.startswith("ls_") and not k.startswith("ls_loss_bwd")]
     if ls:
-        allj["loss_step_fwd"] = {"dram_bytes_per_ray": sum(v["dram_bytes_per_launch"] for v in ls) / 5529600, "from": tag}
+        wi, li = sum(v["warp_inst"] for v in ls), sum(v["lane_inst"] for v in ls)
+        allj["loss_step_fwd"] = {"dram_bytes_per_ray": sum(v["dram_bytes_per_launch"] for v in ls) / RAYS, "from": tag,
+                                 "source_hash": _build.source_hash(), "rays_per_launch": RAYS,
+                                 "warp_inst_per_ray": wi / RAYS, "lane_inst_per_ray": li / RAYS, "lanes_per_inst": li / wi if wi else None,
+                                 "kernel_us_under_ncu": sum(v["duration_us"] for v in ls)}
     json.dump(allj, open(js, "w"), indent=1)
     print("wrote ncu full summary:", list(summ))
