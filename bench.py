@@ -59,6 +59,10 @@ def parse():
     ap.add_argument("--loss-path", default="step", choices=["step", "rec", "dense"],
                     help="step: drt_ray_loss_step (default); rec: three-call route; dense: render_transparent + dense loss")
     ap.add_argument("--unfused-loss", action="store_true", help="same as --loss-path dense")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step (BVH rebuild + fused ray-loss step + backward) as ONE CUDA graph; auto: when a rank has <= 8 M rays "
+                         "per step (launch-bound regime: one view per iteration, or 8 GPUs)")
+    ap.add_argument("--no-iteration", action="store_true", help="skip the supplementary whole-optim.py-iteration timing")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle check of one view of the timed workload")
     ap.add_argument("--shard", default="balanced", choices=["balanced", "roundrobin"],
                     help="views -> ranks: by estimated cost (measured pixels per view, LPT) or k mod N")
@@ -187,6 +191,44 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------
+# NUMA placement of this rank's pinned host buffers (e2e at N > 1: every rank pulls its views over its own PCIe root)
+# ---------------------------------------------------------------------------------------------
+def bind_near_gpu(index):
+    """Best effort, before any pinned allocation: run on the CPUs next to GPU `index` and prefer its NUMA node for new pages.
+    -> dict describing what was possible (containers often expose one node only)."""
+    import ctypes
+    info = {"gpu": index, "numa_node": None, "cpus_before": len(os.sched_getaffinity(0)), "cpu_affinity": "unchanged", "mempolicy": "unchanged"}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:      # nvml pads the domain to 8 hex digits, sysfs uses 4
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info["numa_node"] = node
+        if node >= 0:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            allowed = cpus & os.sched_getaffinity(0)
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                info["cpu_affinity"] = f"{len(allowed)} CPUs of node {node}"
+            else:
+                info["cpu_affinity"] = f"node {node} has no CPU in this process's cpuset"
+            # set_mempolicy(MPOL_PREFERRED = 1, nodemask, maxnode): new pages (cudaHostAlloc included) come from that node
+            mask = ctypes.c_ulong(1 << node)
+            rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+            info["mempolicy"] = f"preferred node {node}" if rc == 0 else f"set_mempolicy failed (errno {ctypes.get_errno()})"
+    except Exception as e:
+        info["error"] = repr(e)
+    return info
+
+
+# ---------------------------------------------------------------------------------------------
 # parity of the timed workload: one whole view of it against the CPU oracle (outside the timed region)
 # ---------------------------------------------------------------------------------------------
 def parity_check(scene, cfg, V, origin_row, d_view, targets_view, image_size, int_ior):
@@ -244,6 +286,74 @@ def parity_check(scene, cfg, V, origin_row, d_view, targets_view, image_size, in
 
 
 # ---------------------------------------------------------------------------------------------
+# supplementary: one whole optim.py iteration (config 3 shape) -- how DRT is actually used
+# ---------------------------------------------------------------------------------------------
+def optim_iteration_bench(dev, mesh_name="mouse_vh", resy=960, resx=1280, n_views=24, iters=30, warmup=5):
+    """optim.py:199-217 per iteration: vertices = init + parameter -> update_verticex (BVH rebuild) -> ray loss on ONE view
+    (optim.py:91-108) + silhouette loss over 8 views (optim.py:67-80) + smoothness (optim.py:82-89) -> backward -> SGD Nesterov
+    step, views resident in HBM, at the Point Grey resolution 960x1280 (optim.py:134, captured_data.py:176-180).
+    -> dict(ms_per_iteration, ms of the three loss terms, rays per iteration)."""
+    import torch
+    import drt_b200.DiffRender as R
+    from drt_b200 import configs, losses, synthetic_data
+    v, f = configs.load_mesh(mesh_name)
+    hp = {"IOR": 1.4723, "ray_w": 40, "sm_w": 0.08, "vh_w": 2e-3, "momentum": 0.95, "start_lr": 0.01}   # config.py:18-39
+    data = synthetic_data.SyntheticData(configs.perturbed_target_mesh(v, scale=0.6), f, resy, resx, n_views=n_views, num_view=n_views,
+                                        cuda_device=dev.index or 0, int_ior=hp["IOR"])
+    data.keep_on_device = True
+    R.intIOR, R.resy, R.resx = hp["IOR"], resy, resx
+    scene = R.Scene(vertices=v, faces=f, cuda_device=dev.index or 0)
+    init = scene.vertices
+    parameter = torch.zeros_like(init, requires_grad=True)
+    parameter.register_hook(lambda g: torch.nan_to_num(g, nan=0.0).clamp(-1.0, 1.0))
+    opt = torch.optim.SGD([parameter], lr=hp["start_lr"], momentum=hp["momentum"], nesterov=True)
+    ray_view, silh_view = data.ray_view_generator(), data.silh_view_generator()
+    compact = {k: data.get_view_compact(k) for k in range(n_views)}
+    for k in range(n_views):
+        data.get_view(k)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    marks = []
+
+    def iteration(record):
+        m = [ev() for _ in range(5)] if record else None
+        opt.zero_grad()
+        if m: m[0].record()
+        scene.update_verticex(init + parameter)
+        ray_loss = losses.ray_loss_view(scene, compact[next(ray_view)])
+        if m: m[1].record()
+        vh_loss = torch.zeros((), dtype=torch.float64, device=dev)
+        for _ in range(8):
+            _, _, sil, origin, _, cam = data.get_view(next(silh_view))
+            edges = scene.silhouette_edge(origin[0])
+            index, output = scene.primary_visibility(edges, cam, origin[0], detach_depth=True)
+            vh_loss = vh_loss + (sil.view(resy, resx)[index[:, 1], index[:, 0]] - output).abs().sum()
+        if m: m[2].record()
+        sm_loss = (-torch.log(1 + scene.dihedral_angle())).sum()
+        loss = hp["ray_w"] * 217.5 / resy / resy * ray_loss + hp["vh_w"] * 217.5 / resy * vh_loss + hp["sm_w"] * scene.mean_len / 10 * sm_loss
+        if m: m[3].record()
+        loss.backward()
+        opt.step()
+        if m:
+            m[4].record()
+            marks.append(m)
+
+    for _ in range(warmup):
+        iteration(False)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        iteration(True)
+    torch.cuda.synchronize(dev)
+    wall = (time.perf_counter() - t0) / iters
+    ph = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / iters for i in range(4)]
+    return {"workload": f"{mesh_name} ({len(f)} tris), one optim.py iteration: 1 ray view {resx}x{resy} + 8 silhouette views + smoothness + backward + SGD step",
+            "ms_per_iteration": sum(ph), "wall_ms_per_iteration": 1e3 * wall, "iterations": iters,
+            "phases_ms": {"rebuild+ray_loss": ph[0], "silhouette_8_views": ph[1], "smoothness+total": ph[2], "backward+sgd": ph[3]},
+            "primary_rays_per_iteration": resy * resx, "rays_per_s": resy * resx / (sum(ph) * 1e-3),
+            "note": "device time between CUDA events; the silhouette path syncs once per view (data-dependent output sizes, as in the reference)"}
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -263,6 +373,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: drt_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_near_gpu(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -368,6 +479,45 @@ def run_b200(args):
         if world > 1:
             ddist.allreduce_grad(V.grad)
     sync_all()
+    # The ~30 launches of a step (LBVH rebuild, 8 kernels of the fused ray-loss step, the autograd scale) captured ONCE as a CUDA
+    # graph and replayed: same kernels, same arguments (the library's scratch and torch's graph pool are static), no Python or
+    # launch overhead between them.  The all-reduce stays outside (its epoch is a kernel argument that changes every call).
+    probe = None
+    use_graph = args.loss_path == "step" and n_local > 0 and (args.graph == "on" or (args.graph == "auto" and n_local <= 8_000_000))
+    graph = None
+    if use_graph:
+        # phase split (build / forward / backward) from a few stream-launched steps: a graph has no event boundaries inside
+        pm = [[ev() for _ in range(6)] for _ in range(3)]
+        for m in pm:
+            m[2].record()
+        for m in pm:
+            loss_buf.zero_()
+            step(origin, ray_dir, screen, valid, g_dir, m)
+            m[5].record()
+        torch.cuda.synchronize(dev)
+        probe = [sum(m[i].elapsed_time(m[i + 1]) for m in pm) / len(pm) for i in range(5)]
+        try:
+            V.grad = None
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):          # warm the capture stream's allocator, as torch's graph recipe asks
+                    loss_buf.zero_()
+                    step(origin, ray_dir, screen, valid, g_dir)
+                V.grad = None
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss_buf.zero_()
+                step(origin, ray_dir, screen, valid, g_dir)
+            for _ in range(2):
+                graph.replay()
+            sync_all()
+        except Exception as e:
+            sys.stderr.write(f"bench.py: CUDA graph capture failed ({e!r}); timing the stream-launched step\n")
+            graph = None
+            V.grad = None
+            torch.cuda.synchronize(dev)
     with torch.no_grad():
         valid_frac = float(scene.render_transparent(origin, ray_dir)[2][:, 0].float().mean().item()) if n_local else 0.0
     sampler = ClockSampler(local)
@@ -383,8 +533,14 @@ def run_b200(args):
     start, end = ev(), ev()
     start.record()
     for k in range(args.steps):
-        loss_buf.zero_()
-        step(origin, ray_dir, screen, valid, g_dir, marks[k])
+        if graph is not None:
+            marks[k][0].record()
+            graph.replay()
+            for j in (1, 2, 3, 4):          # no phase boundaries inside a graph: build / fwd / bwd come from the ncu launch list
+                marks[k][j].record()
+        else:
+            loss_buf.zero_()
+            step(origin, ray_dir, screen, valid, g_dir, marks[k])
         if world > 1:
             ddist.allreduce_grad(V.grad)
         marks[k][5].record()
@@ -397,6 +553,8 @@ def run_b200(args):
     sync_all()
     t_total_ms = start.elapsed_time(end)
     phases = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / args.steps for i in range(5)]
+    if graph is not None:  # kernel-level phases come from the stream-launched probe steps; the all-reduce phase from the timed ones
+        phases = probe[:4] + [phases[4]]
     if args.loss_path == "step":  # marks[2] = end of the forward wavefront (recorded by the library), marks[4] = end of backward
         phases[3] = phases[2] + phases[3]
         phases[2] = 0.0
@@ -669,9 +827,38 @@ def run_b200(args):
             torch.cuda.synchronize(dev)
             if j >= 2:
                 t_ref += a.elapsed_time(b)
-        ref_gpu = {"value": n_ref * n_pix / (t_ref * 1e-3), "unit": UNIT, "ms_per_view": t_ref / n_ref, "views": n_ref,
+        # how big the op chain is: ATen calls (nested ones included) and CUDA kernels of ONE forward+backward, counted by the
+        # profiler outside the timed loop; the reference's own DiffRender.py records 1 143 forward / 515 backward ATen calls
+        # (nested included; 517 / 177 top-level) for the same path
+        ops = None
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            Vr.grad = None
+            with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+                oo, od, mk = chain_torch.render_transparent(Vr, faces_t, o_v, d_v, isect, configs.INT_IOR)
+                tg = scr_v - oo.detach()
+                tg = tg / tg.norm(dim=1, keepdim=True)
+                ((od - tg)[mk[:, 0]]).pow(2).sum().backward()
+                torch.cuda.synchronize(dev)
+            evs = prof.events()
+            ops = {"aten_calls_incl_nested": sum(1 for e in evs if e.name.startswith("aten::")),
+                   "cuda_kernels": sum(1 for e in evs if str(e.device_type).endswith("CUDA")),
+                   "reference_aten_calls_incl_nested": {"forward": 1143, "backward": 515, "source": "SURVEY.md App. C, DiffRender.py unmodified on CPU"}}
+        except Exception as e:
+            ops = {"error": repr(e)}
+        ref_gpu = {"value": n_ref * n_pix / (t_ref * 1e-3), "unit": UNIT, "ms_per_view": t_ref / n_ref, "views": n_ref, "op_counts": ops,
                    "kind": "reference op chain (PyTorch autograd, oracle/chain_torch.py) + drt_closest_hit as the intersector, "
-                           "one view per iteration; supplementary, not the driver's reference arm"}
+                           "one view per iteration; supplementary, not the driver's reference arm.  chain_torch is a STREAMLINED restatement (fewer ops "
+                           "than the reference's DiffRender.py: no dead Reflect / Fresnel R, no assert syncs), so this number flatters the reference's approach"}
+        scene.update_verticex(V)
+
+    # ---- supplementary: a whole optim.py iteration on the config-3 mesh (rank 0, N=1 only) -------------------
+    optim_iter = None
+    if rank == 0 and world == 1 and not args.no_iteration:
+        try:
+            optim_iter = optim_iteration_bench(dev)
+        except Exception as e:  # supplementary: never takes the headline line down
+            optim_iter = {"error": repr(e)}
         scene.update_verticex(V)
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------
@@ -746,18 +933,20 @@ def run_b200(args):
                        "parallelism": f"views sharded over {world} GPU(s), mesh/BVH replicated, 1 all-reduce of grad_V",
                        "allreduce": ("none" if world == 1 else "peer-memory one-shot kernel (drt_comm_*)" if ddist.peer_allreduce(1, dev) is not None else "torch.distributed/NCCL"),
                        "bvh": "refit each step" if args.refit else "full LBVH rebuild each step", "loss_path": args.loss_path,
+                       "launch": "one CUDA graph replay per step" if graph is not None else "stream launches",
                        "l2": "inputs larger than L2 (%.1f GB of rays per step per GPU)" % (n_local * 48 / 1e9),
                        "int_ior": configs.INT_IOR, "valid_frac_rank0": valid_frac},
-            "phases_ms": {"bvh_build": t_build_ms, "fwd": t_fwd_ms, "loss_grad": phases[2], "bwd": t_bwd_ms, "allreduce": t_ar_ms},
+            "phases_ms": {"bvh_build": t_build_ms, "fwd": t_fwd_ms, "loss_grad": phases[2], "bwd": t_bwd_ms, "allreduce": t_ar_ms,
+                          "source": "3 stream-launched probe steps (the timed steps replay one CUDA graph)" if graph is not None else "the timed steps"},
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "e2e_vs_cpu_baseline": ({"compact_layout": e2e["value"] / cpu["value"] if e2e else None,
                                      "reference_layout": (e2e_ref_layout or e2e)["value"] / cpu["value"] if (e2e_ref_layout or e2e) else None,
                                      "note": "e2e (host buffers, copies timed) over the CPU port on this box's host cores; `e2e` is the loader's lossless compact "
                                              "layout (26 B/ray), `e2e_reference_layout` the reference's dense per-view tensors (73 B/ray): quote both"}
                                     if cpu and (e2e or e2e_ref_layout) else None),
-            "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "e2e": e2e, "e2e_reference_layout": e2e_ref_layout, "e2e_pinhole": e2e_pinhole, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "optim_iteration": optim_iter, "e2e": e2e, "e2e_reference_layout": e2e_ref_layout, "e2e_pinhole": e2e_pinhole, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "loss": loss_val, "grad_norm": grad_norm,
-            "stage_counts_rank0": stage_counts, "parity_check": parity, "allreduce_check": ar_check, "shard": {"policy": args.shard if world > 1 else "none", "skew": shard_skew},
+            "stage_counts_rank0": stage_counts, "parity_check": parity, "allreduce_check": ar_check, "shard": {"policy": args.shard if world > 1 else "none", "skew": shard_skew}, "numa_rank0": numa,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -56,10 +56,24 @@ typedef float4 node_quad;
 #endif
 constexpr int kTriD2 = 5;
 constexpr int kSceneWords = 16;
+constexpr int kEmptyLink = 0x7fffffff;  // link of an empty wide-node slot (its box can never be entered)
 constexpr float kGridSteps = 65520.f;  // steps across the root box; 7 spare steps on the low side, 8 on the high side
+
+// DRT_BVH4: a 4-WIDE view of the same tree for the persistent query kernels.  Wide node i (64 B = 4 x uint4) holds the
+// GRANDCHILDREN of binary node i: slots 0,1 = the children of its left child, slots 2,3 = those of its right child (a child that
+// is a leaf fills one slot of its pair, the other slot is an empty box that no ray can enter), planes quantised exactly like
+// the binary layout:   X = (x of slot 0..3 as lo | hi << 16)   Y   Z   L = (link of slot 0..3).
+// One wide step = one dependent fetch where the binary walk needs two; the query kernels are bound by the latency of those
+// fetches (ncu, r02a: long-scoreboard stalls, 59 % issue slots busy, 17 of 32 lanes), not by their instruction count.  The
+// push order (nearer pair first, nearer member first) is the order the binary walk takes, so the visit order is unchanged.
+// Links are binary node numbers, so an entry point found by the beam pass on the binary nodes is valid here too.
+#ifndef DRT_BVH4
+#define DRT_BVH4 0  // measured on B200 at C4: forward 5.14 ms wide vs 5.18 ms binary (the wide step executes as many instructions as the two binary steps it replaces) -- kept as a tested option
+#endif
 
 struct BvhView {
     const node_quad* nodes;
+    const uint4* nodes4;   // [nNodes][4] wide nodes (DRT_BVH4), else nullptr
     const double2* tris;
     const int32_t* F;      // [nF,3] original faces
     const unsigned* scene; // scene[7] = float bits of pmax
@@ -291,6 +305,53 @@ __global__ void emit_nodes_kernel(int n, const int2* __restrict__ children, cons
     uint4* node = nodes + (size_t)i * kNodeQuads;
     node[0] = make_uint4(qpair(l0.x, h0.x, gx, ix), qpair(l1.x, h1.x, gx, ix), qpair(l0.y, h0.y, gy, iy), qpair(l1.y, h1.y, gy, iy));
     node[1] = make_uint4(qpair(l0.z, h0.z, gz, iz), qpair(l1.z, h1.z, gz, iz), (unsigned)c0, (unsigned)c1);
+}
+// wide node i from binary node i (see BvhView::nodes4); boxes are read through L2 (also called from the cooperative build)
+__device__ __forceinline__ void emit_wide_node(int i, int n, const int2* __restrict__ children, const float4* blo, const float4* bhi,
+                                               const float g0[3], const float inv_s[3], uint4* __restrict__ nodes4)
+{
+    unsigned X[4], Y[4], Z[4], L[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { X[s] = Y[s] = Z[s] = 0x0000ffffu; L[s] = (unsigned)kEmptyLink; }  // lo = 65535, hi = 0: never entered
+    auto put = [&](int s, int c) {  // c in build numbering: internal < n-1 <= leaf
+        const float4 l = __ldcg(&blo[c]), h = __ldcg(&bhi[c]);
+        X[s] = qpair(l.x, h.x, g0[0], inv_s[0]);
+        Y[s] = qpair(l.y, h.y, g0[1], inv_s[1]);
+        Z[s] = qpair(l.z, h.z, g0[2], inv_s[2]);
+        L[s] = (unsigned)(c >= n - 1 ? ~(c - (n - 1)) : c);
+    };
+    if (n == 1) {
+        put(0, 0);  // the only leaf (build number n-1 = 0)
+    } else {
+        const int2 ch = children[i];
+        const int side[2] = {ch.x, ch.y};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int c = side[k];
+            if (c >= n - 1) put(2 * k, c);
+            else {
+                const int2 g = children[c];
+                put(2 * k, g.x);
+                put(2 * k + 1, g.y);
+            }
+        }
+    }
+    uint4* node = nodes4 + (size_t)i * 4;
+    node[0] = make_uint4(X[0], X[1], X[2], X[3]);
+    node[1] = make_uint4(Y[0], Y[1], Y[2], Y[3]);
+    node[2] = make_uint4(Z[0], Z[1], Z[2], Z[3]);
+    node[3] = make_uint4(L[0], L[1], L[2], L[3]);
+}
+
+__global__ void emit_nodes4_kernel(int n, const int2* __restrict__ children, const float4* __restrict__ blo, const float4* __restrict__ bhi,
+                                   const unsigned* __restrict__ scene, uint4* __restrict__ nodes4)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n > 1 ? n - 1 : 1)) return;
+    const float g0[3] = {__uint_as_float(scene[8]), __uint_as_float(scene[9]), __uint_as_float(scene[10])};
+    const float inv_s[3] = {__fdiv_rn(1.f, __uint_as_float(scene[11])), __fdiv_rn(1.f, __uint_as_float(scene[12])),
+                            __fdiv_rn(1.f, __uint_as_float(scene[13]))};
+    emit_wide_node(i, n, children, blo, bhi, g0, inv_s, nodes4);
 }
 #else
 __global__ void emit_nodes_kernel(int n, const int2* __restrict__ children, const float4* __restrict__ blo,

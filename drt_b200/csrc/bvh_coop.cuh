@@ -32,6 +32,7 @@ struct BuildArgs {
     int* flags;
     unsigned* scene;
     node_quad* nodes;
+    uint4* nodes4;       // wide nodes (DRT_BVH4), may be null
     double2* tris;
     int refit;           // 1: keep keys / topology, run fit + emit only
 };
@@ -318,6 +319,10 @@ __global__ void __launch_bounds__(kSortThreads) lbvh_build_kernel(BuildArgs a)
             node[0] = make_uint4(qpair(l0.x, h0.x, g0[0], ix), qpair(l1.x, h1.x, g0[0], ix), qpair(l0.y, h0.y, g0[1], iy), qpair(l1.y, h1.y, g0[1], iy));
             node[1] = make_uint4(qpair(l0.z, h0.z, g0[2], iz), qpair(l1.z, h1.z, g0[2], iz), (unsigned)c0, (unsigned)c1);
         }
+    }
+    if (a.nodes4) {
+        const float inv_s[3] = {ix, iy, iz};
+        for (int i = tid; i < (n > 1 ? n - 1 : 1); i += nth) emit_wide_node(i, n, a.children, a.blo, a.bhi, g0, inv_s, a.nodes4);
     }
 #endif
     for (int k = tid; k < n; k += nth) {

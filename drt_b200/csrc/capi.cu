@@ -167,9 +167,10 @@ struct drt_bvh {
     uint64_t* sorted_keys = nullptr;             // the half of `keys` that holds the sorted (Morton, id) keys
     // traversal data
     node_quad* nodes = nullptr; size_t capN = 0;
+    uint4* nodes4 = nullptr;   size_t capN4 = 0;  // 4-wide view of the same tree (DRT_BVH4)
     double2* tris = nullptr;   size_t capT = 0;
 
-    BvhView view() const { return BvhView{nodes, tris, F, scene, nF}; }
+    BvhView view() const { return BvhView{nodes, nodes4, tris, F, scene, nF}; }
 };
 
 namespace {
@@ -244,7 +245,7 @@ __global__ void init_scene_kernel(unsigned* scene, bool reset_bad)
 int coop_build(drt_bvh* b, const double* V64, int refit, cudaStream_t st)
 {
     const int n = b->nF;
-    BuildArgs a{b->F, b->V32, V64, b->nV, n, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris, refit};
+    BuildArgs a{b->F, b->V32, V64, b->nV, n, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->nodes4, b->tris, refit};
     const int64_t work = std::max<int64_t>(n, V64 ? 3 * (int64_t)b->nV : 0);
     // a small grid keeps the grid-wide barriers short: one block per SM at most
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_for(work, kSortThreads), std::min(b->sm_count, b->sm_count * b->build_blocks_per_sm)));
@@ -269,6 +270,9 @@ int fit_and_emit(drt_bvh* b, cudaStream_t st, const double* pending_V64 = nullpt
                                                     b->flags); ++g_launches;
     grid_kernel<<<1, 32, 0, st>>>(b->blo, b->bhi, b->scene); ++g_launches;
     emit_nodes_kernel<<<blocks_for(n > 1 ? n - 1 : 1, 256), 256, 0, st>>>(n, b->children, b->blo, b->bhi, b->scene, b->nodes); ++g_launches;
+#if DRT_QNODE && DRT_BVH4
+    emit_nodes4_kernel<<<blocks_for(n > 1 ? n - 1 : 1, 256), 256, 0, st>>>(n, b->children, b->blo, b->bhi, b->scene, b->nodes4); ++g_launches;
+#endif
     emit_tris_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_keys, n, b->tris); ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;
@@ -297,6 +301,9 @@ int build_tree(drt_bvh* b, cudaStream_t st, const double* pending_V64 = nullptr)
     if ((rc = ensure(b->flags, b->capFl, (size_t)n))) return rc;
     if ((rc = ensure(b->nodes, b->capN, (size_t)kNodeQuads * (size_t)(n > 1 ? n - 1 : 1)))) return rc;
     if ((rc = ensure(b->tris, b->capT, (size_t)kTriD2 * (size_t)n))) return rc;
+#if DRT_QNODE && DRT_BVH4
+    if ((rc = ensure(b->nodes4, b->capN4, 4 * (size_t)(n > 1 ? n - 1 : 1)))) return rc;
+#endif
     if (DRT_QNODE && tuning().coop_build && b->build_blocks_per_sm > 0) return coop_build(b, pending_V64, 0, st);
     if (pending_V64) {
         cast_vertices_kernel<<<blocks_for(3 * (int64_t)b->nV, 256), 256, 0, st>>>(pending_V64, b->V32, 3 * b->nV);
@@ -412,7 +419,7 @@ int drt_bvh_destroy(drt_bvh* b)
     if (!b) return DRT_OK;
     DeviceGuard g(b->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {b->listA, b->listB, b->park, b->listM, b->listS, b->tbucket, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->tris};
+    void* ptrs[] = {b->listA, b->listB, b->park, b->listM, b->listS, b->tbucket, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->nodes4, b->tris};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete b;

@@ -110,11 +110,17 @@ struct LossEntryJob {
     __device__ __forceinline__ int ray_of(int item) const { return tiles.ray_of(item); }
     __device__ __forceinline__ bool load(int item, d3& o, d3& d) const
     {
-        const int i = ray_of(item);
-        o = rays.o(i);
-        d = rays.d(i);
+        load_ray(ray_of(item), o, d);
         return true;
     }
+    __device__ __forceinline__ void load_ray(int i, d3& o, d3& d) const  // by ray index
+    {
+        o = rays.o(i);
+        d = rays.d(i);
+    }
+    __device__ __forceinline__ bool same_origin_row(int i, int j) const { return rays.rpo > 1 && i / rays.rpo == j / rays.rpo; }
+    __device__ __forceinline__ d3 origin_of(int i) const { return rays.o(i); }
+    __device__ __forceinline__ d3 dir_of(int i) const { return rays.d(i); }
     __device__ __forceinline__ void retire(int item, int id, double) const
     {
         int slot = warp_append<>(countL, id >= 0);

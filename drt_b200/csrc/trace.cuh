@@ -8,7 +8,13 @@
 
 namespace drt {
 
-constexpr int kStackDepth = 96 + 8;  // binary Karras depth <= 63 key bits + 32 index bits, + deferred leaves
+constexpr int kStackDepth = 96 + 8;
+// leaves a lane may queue before its triangle tests run (see "Leaves are DEFERRED" below)
+#ifndef DRT_DEFER
+#define DRT_DEFER 3
+#endif
+constexpr int kDefer = DRT_DEFER;
+static_assert(kDefer >= 1 && kDefer <= 4, "the shared-memory leaf queue has 4 slots");  // binary Karras depth <= 63 key bits + 32 index bits, + deferred leaves
 constexpr int kDone = INT_MIN;
 
 struct QRay {        // query ray = float32 cast of the chain's float64 ray (DiffRender.py:387-388)
@@ -247,9 +253,31 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
 #endif
 }
 
-// one binary node: test both children, continue with the nearer hit, push the other
+// one binary node: test both children, continue with the nearer hit, push the other.
+// DRT_INLINE_LEAF: a hit child that is a LEAF goes straight into the lane's leaf queue when there is room, instead of being
+// returned as the next "node" and costing a loop iteration of its own -- ncu (r02a, exit query) shows 15 % of the warp
+// instructions in those leaf-push iterations running with 3-4 of 32 lanes while the other lanes wait.
+#ifndef DRT_INLINE_LEAF
+#define DRT_INLINE_LEAF 0  // measured on B200 at C4: forward 5.49 ms with it, 5.18 without (the extra predicated work in EVERY node step costs more than the leaf iterations it removes)
+#endif
+// DRT_PREFETCH_TRI: when a leaf is queued, pull its 80-byte triangle record towards L1 -- every queued leaf IS tested a few
+// node steps later, and ncu (r02a) shows the first float64 instructions of the triangle test waiting on those loads
+// (7.5 % of the exit query's stall samples).
+#ifndef DRT_PREFETCH_TRI
+#define DRT_PREFETCH_TRI 0
+#endif
+__device__ __forceinline__ void prefetch_tri(const BvhView& B, int leaf)
+{
+#if DRT_PREFETCH_TRI
+    const char* p = reinterpret_cast<const char*>(B.tris + (size_t)(~leaf) * kTriD2);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 64));
+#else
+    (void)B; (void)leaf;
+#endif
+}
 template <class S>
-__device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float tmax, int node, S& stack, int& sp)
+__device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float tmax, int node, S& stack, int& sp, int& nd)
 {
     const uint4* p = B.nodes + (size_t)node * kNodeQuads;
 #if DRT_LDG256
@@ -281,12 +309,16 @@ __device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float 
     const float N1 = fmaxf(fmaxf(n1.x, n1.y), fmaxf(z1.x, 0.f));
     const float F1 = fminf(fminf(f1.x, f1.y), fminf(z1.y, tmax));
 #if DRT_FOLD_E
-    const bool h0 = N0 <= F0, h1 = N1 <= F1;
+    bool h0 = N0 <= F0, h1 = N1 <= F1;
 #else
-    const bool h0 = N0 <= fmaf(F0, 1.00000095367431640625f, q.E);
-    const bool h1 = N1 <= fmaf(F1, 1.00000095367431640625f, q.E);
+    bool h0 = N0 <= fmaf(F0, 1.00000095367431640625f, q.E);
+    bool h1 = N1 <= fmaf(F1, 1.00000095367431640625f, q.E);
 #endif
     const int c0 = (int)b.z, c1 = (int)b.w;
+#if DRT_INLINE_LEAF
+    if (h0 && c0 < 0 && nd < kDefer) { stack.leaf_put(nd, c0); ++nd; h0 = false; prefetch_tri(B, c0); }
+    if (h1 && c1 < 0 && nd < kDefer) { stack.leaf_put(nd, c1); ++nd; h1 = false; prefetch_tri(B, c1); }
+#endif
     if (h0 && h1) {
         const bool first0 = N0 <= N1;
         const int later = first0 ? c1 : c0;
@@ -301,6 +333,53 @@ __device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float 
     if (h1) return c1;
     return stack.pop_or(sp, kDone);
 }
+#if DRT_BVH4
+// one WIDE node (BvhView::nodes4): test the four grandchild boxes, continue with the nearest hit of the nearer pair, push the
+// others so that they pop in the order the binary walk would visit them (nearer pair first, nearer member first)
+template <class S>
+__device__ __forceinline__ int node_step4(const BvhView& B, const RayQ& q, float tmax, int node, S& stack, int& sp, int& nd)
+{
+    const uint4* p = B.nodes4 + (size_t)node * 4;
+    const uint4 X = __ldg(p), Y = __ldg(p + 1), Z = __ldg(p + 2), L = __ldg(p + 3);
+    const unsigned fx = q.sx ^ 0x22u, fy = q.sy ^ 0x22u, fz = q.sz ^ 0x22u;
+    const float2 Axy = make_float2(q.ix, q.iy), Cxy = make_float2(q.cx, q.cy), Azz = make_float2(q.iz, q.iz), Czz = make_float2(q.cz, q.cz);
+    float d[4];
+    bool h[4];
+    const unsigned xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const float2 n = fma2(make_float2(qplane(xs[s], q.sx), qplane(ys[s], q.sy)), Axy, Cxy);
+        const float2 f = fma2(make_float2(qplane(xs[s], fx), qplane(ys[s], fy)), Axy, Cxy);
+        const float2 z = fma2(make_float2(qplane(zs[s], q.sz), qplane(zs[s], fz)), Azz, Czz);
+        const float N = fmaxf(fmaxf(n.x, n.y), fmaxf(z.x, 0.f));
+        const float F = fminf(fminf(f.x, f.y), fminf(z.y, tmax));
+        h[s] = N <= fmaf(F, 1.00000095367431640625f, q.E);
+        d[s] = h[s] ? N : INFINITY;
+    }
+#if DRT_INLINE_LEAF
+    {
+        const int ls[4] = {(int)L.x, (int)L.y, (int)L.z, (int)L.w};
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (h[s] && ls[s] < 0 && nd < kDefer) { stack.leaf_put(nd, ls[s]); ++nd; h[s] = false; d[s] = INFINITY; prefetch_tri(B, ls[s]); }
+    }
+#endif
+    const bool s01 = d[1] < d[0], s23 = d[3] < d[2];
+    const float m01 = fminf(d[0], d[1]), m23 = fminf(d[2], d[3]);
+    const int near01 = s01 ? (int)L.y : (int)L.x, far01 = s01 ? (int)L.x : (int)L.y;
+    const int near23 = s23 ? (int)L.w : (int)L.z, far23 = s23 ? (int)L.z : (int)L.w;
+    const bool both01 = h[0] && h[1], any01 = h[0] || h[1], both23 = h[2] && h[3], any23 = h[2] || h[3];
+    const bool swap = m23 < m01;  // the right pair is entered first
+    const int nearP = swap ? near23 : near01, farP = swap ? far23 : far01, nearQ = swap ? near01 : near23, farQ = swap ? far01 : far23;
+    const bool bothP = swap ? both23 : both01, anyP = swap ? any23 : any01, bothQ = swap ? both01 : both23, anyQ = swap ? any01 : any23;
+    if (bothQ) stack.push(sp, farQ);
+    if (anyQ) stack.push(sp, nearQ);
+    if (bothP) stack.push(sp, farP);
+    if (anyP) return nearP;
+    return stack.pop_or(sp, kDone);
+}
+#endif
+
 #else
 __device__ __forceinline__ float safe_inv(float d)
 {
@@ -323,8 +402,9 @@ __device__ __forceinline__ RayQ ray_setup(const BvhView& B, const QRay& r)
 
 // one binary node: test both children, continue with the nearer hit, push the other
 template <class S>
-__device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float tmax, int node, S& stack, int& sp)
+__device__ __forceinline__ int node_step(const BvhView& B, const RayQ& q, float tmax, int node, S& stack, int& sp, int& nd)
 {
+    (void)nd;
     const float4* p = B.nodes + (size_t)node * kNodeQuads;
     const float4 nx = __ldg(p), ny = __ldg(p + 1), nz = __ldg(p + 2);
     const float4 nl = __ldg(p + 3);
@@ -483,11 +563,6 @@ __device__ __forceinline__ bool leaf_step(const BvhView& B, const RayQ& q, int l
 // whose box passed the test is still tested, and ties still resolve to the lowest id.
 // Depth: with every lane filling its own queue (walk) 2 was best (1: -9 %, 4: -1 %, 8: -6 % at C4); with the
 // warp vote (walk_vote) 3 is (C4 forward 6.43 ms at 3 vs 6.55 at 2 and 6.47 at 4, vote 8).
-#ifndef DRT_DEFER
-#define DRT_DEFER 3
-#endif
-constexpr int kDefer = DRT_DEFER;
-static_assert(kDefer >= 1 && kDefer <= 4, "the shared-memory leaf queue has 4 slots");
 
 // DRT_FULLQ_WALK = 1: a lane whose leaf queue is full keeps walking internal nodes and blocks only when the next LEAF arrives
 // (one test on the hot path); 0: it blocks as soon as the queue is full, so its triangles are tested -- and tmax shrinks --
@@ -505,23 +580,28 @@ __device__ __forceinline__ bool can_step(int node, int nd)
 }
 
 // one node step or one leaf push (the caller checked can_step)
-template <class S>
+template <bool WIDE, class S>
 __device__ __forceinline__ void advance(const BvhView& B, const RayQ& q, float tmax, int& node, S& stack, int& sp, int& nd)
 {
     if (node >= 0) {
-        node = node_step(B, q, tmax, node, stack, sp);
+#if DRT_QNODE && DRT_BVH4
+        node = WIDE ? node_step4(B, q, tmax, node, stack, sp, nd) : node_step(B, q, tmax, node, stack, sp, nd);
+#else
+        node = node_step(B, q, tmax, node, stack, sp, nd);
+#endif
     } else {
         stack.leaf_put(nd, node);
+        prefetch_tri(B, node);
         ++nd;
         node = stack.pop_or(sp, kDone);
     }
 }
 
 // walk until the stack is exhausted or the lane is blocked by its full leaf queue
-template <class S>
+template <bool WIDE = false, class S>
 __device__ __forceinline__ void walk(const BvhView& B, const RayQ& q, float tmax, int& node, S& stack, int& sp, int& nd)
 {
-    while (can_step(node, nd)) advance(B, q, tmax, node, stack, sp, nd);
+    while (can_step(node, nd)) advance<WIDE>(B, q, tmax, node, stack, sp, nd);
 }
 
 // Same walk with a WARP VOTE on when to stop: lanes step together, kVoteEvery node steps (or leaf pushes) per vote, and the
@@ -534,15 +614,19 @@ __device__ __forceinline__ void walk(const BvhView& B, const RayQ& q, float tmax
 #define DRT_VOTE_EVERY 3
 #endif
 constexpr int kVoteEvery = DRT_VOTE_EVERY;
+#ifndef DRT_VOTE_EVERY4
+#define DRT_VOTE_EVERY4 2  // wide steps per vote
+#endif
+constexpr int kVoteEvery4 = DRT_VOTE_EVERY4;
 
-template <class S>
+template <bool WIDE = false, class S>
 __device__ __forceinline__ void walk_vote(const BvhView& B, const RayQ& q, float tmax, int& node, S& stack, int& sp, int& nd, int vote)
 {
     const unsigned FULL = 0xffffffffu;
     for (;;) {
 #pragma unroll
-        for (int u = 0; u < kVoteEvery; ++u)
-            if (can_step(node, nd)) advance(B, q, tmax, node, stack, sp, nd);
+        for (int u = 0; u < (WIDE ? kVoteEvery4 : kVoteEvery); ++u)
+            if (can_step(node, nd)) advance<WIDE>(B, q, tmax, node, stack, sp, nd);
         const bool cont = can_step(node, nd);
         if (!__any_sync(FULL, cont) || __popc(__ballot_sync(FULL, nd > 0 && !cont)) >= vote) break;
     }

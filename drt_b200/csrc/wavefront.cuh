@@ -26,6 +26,13 @@ namespace drt {
 #endif
 constexpr int kFetchBatch = DRT_FETCH_BATCH;
 
+// the persistent query kernels walk the 4-wide view of the tree when it is built (bvh.cuh: DRT_BVH4)
+#if DRT_QNODE && DRT_BVH4
+constexpr bool kWideQueries = true;
+#else
+constexpr bool kWideQueries = false;
+#endif
+
 template <typename Dummy = void>
 __device__ __forceinline__ int warp_append(int* __restrict__ counter, bool pred)
 {
@@ -96,8 +103,8 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
         const int need = min(thresh, __popc(live));
 
         for (;;) {
-            if (vote) walk_vote(B, q, tmax, node, stack, sp, nd, vote);
-            else walk(B, q, tmax, node, stack, sp, nd);
+            if (vote) walk_vote<kWideQueries>(B, q, tmax, node, stack, sp, nd, vote);
+            else walk<kWideQueries>(B, q, tmax, node, stack, sp, nd);
             if (drain<ANY>(B, q, stack, nd, t_best, id_best, tmax)) { node = kDone; stack.reset(sp); }
             unsigned fin = __ballot_sync(FULL, item >= 0 && node == kDone);
             if (__popc(fin) >= need) break;
@@ -151,10 +158,21 @@ __device__ __forceinline__ void beam_pass(const BvhView& B, Job& job, int total,
         bool has_rays = false, shared_origin = true;
         if ((int)lane < tpb) {
             const int first = base + 32 * (int)lane;
+            // the 32 work items of a tile map to rays r0 + row * img_w + col (TileMap): one index computation per tile, not per ray
+            const int r0 = job.tiles.ray_of(first);
+            const int tw_log2 = job.tiles.tw_log2, tw_mask = (1 << tw_log2) - 1, row_stride = job.tiles.img_w;
+            // rays that provably read the same origin row (one row per view, captured_data.py:38) need it once per tile
+            const int r_last = row_stride ? r0 + (31 >> tw_log2) * row_stride + tw_mask : r0 + 31;
+            const bool one_row = first + 31 < total && job.same_origin_row(r0, r_last);
+            d3 o_tile = mk3(0, 0, 0);
+            if (one_row) o_tile = job.origin_of(r0);
 #pragma unroll 4
             for (int j = 0; j < 32; ++j) {
-                d3 o, d;
-                if (first + j < total && job.load(first + j, o, d)) {
+                d3 o = o_tile, d;
+                if (first + j < total) {
+                    const int i = row_stride ? r0 + (j >> tw_log2) * row_stride + (j & tw_mask) : r0 + j;
+                    if (one_row) d = job.dir_of(i);
+                    else job.load_ray(i, o, d);
                     const QRay r = cast_ray(o, d);
                     if (!has_rays) { box = r.ox; boy = r.oy; boz = r.oz; has_rays = true; }
                     shared_origin = shared_origin && r.ox == box && r.oy == boy && r.oz == boz;
@@ -216,8 +234,8 @@ __device__ __forceinline__ void entry_query_tiles(const BvhView& B, Job& job, in
             q = ray_setup(B, QRay{0.f, 0.f, 0.f, 1.f, 1.f, 1.f});
         }
         for (;;) {
-            if (vote) walk_vote(B, q, tmax, node, stack, sp, nd, vote);
-            else walk(B, q, tmax, node, stack, sp, nd);
+            if (vote) walk_vote<kWideQueries>(B, q, tmax, node, stack, sp, nd, vote);
+            else walk<kWideQueries>(B, q, tmax, node, stack, sp, nd);
             drain<false>(B, q, stack, nd, t_best, id_best, tmax);
             if (!__any_sync(FULL, node != kDone)) break;
         }
@@ -258,11 +276,17 @@ struct EntryJob {
     TileMap tiles;  // work item -> ray (8 x 4 pixel tiles when the image size is known)
     __device__ __forceinline__ bool load(int item, d3& o, d3& d) const
     {
-        const int i = tiles.ray_of(item);
-        o = ld3(origin + 3 * (int64_t)i);
-        d = ld3(dir + 3 * (int64_t)i);
+        load_ray(tiles.ray_of(item), o, d);
         return true;
     }
+    __device__ __forceinline__ void load_ray(int i, d3& o, d3& d) const  // by ray index
+    {
+        o = ld3(origin + 3 * (int64_t)i);
+        d = ld3(dir + 3 * (int64_t)i);
+    }
+    __device__ __forceinline__ bool same_origin_row(int, int) const { return false; }  // one origin row per ray: compare the data
+    __device__ __forceinline__ d3 origin_of(int i) const { return ld3(origin + 3 * (int64_t)i); }
+    __device__ __forceinline__ d3 dir_of(int i) const { return ld3(dir + 3 * (int64_t)i); }
     __device__ __forceinline__ void retire(int item, int id, double) const
     {
         const int i = tiles.ray_of(item);

@@ -104,14 +104,14 @@ class PeerAllReduce:
 
 
 _peer = {}
-PEER_DEFAULT_MAX_WORLD = 4
+PEER_DEFAULT_MAX_WORLD = 8
 
 
 def peer_allreduce(numel, device, group=None):
     """The process-wide PeerAllReduce for tensors of up to `numel` doubles (created collectively on first use).
-    DRT_ALLREDUCE=nccl disables it, =peer forces it; by default it is used up to the 4 ranks it has been measured
-    at on B200 (bit-exact rank-order sums; step time equal to NCCL's at 2 and 4 GPUs -- the all-reduce phase of a
-    step is dominated by the ranks' arrival skew, not by the collective) and NCCL is used above."""
+    DRT_ALLREDUCE=nccl disables it, =peer forces it; by default it is used for all the GPUs of one box (up to 8 ranks:
+    bit-exact rank-order sums; the all-reduce phase of a step is dominated by the ranks' arrival skew, not by the
+    collective) and NCCL is used above or across hosts."""
     mode = os.environ.get("DRT_ALLREDUCE", "").lower()
     if mode in ("nccl", "torch") or (mode != "peer" and dist.get_world_size(group) > PEER_DEFAULT_MAX_WORLD):
         return None

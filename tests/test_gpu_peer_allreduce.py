@@ -58,7 +58,7 @@ def test_peer_allreduce_two_or_more_gpus():
     n_gpu = torch.cuda.device_count()
     if n_gpu < 2:
         pytest.skip("needs >= 2 GPUs on one box")
-    world = min(n_gpu, 4)   # the sizes the kernel has been run at on B200 so far (2 and 4); dist.PEER_DEFAULT_MAX_WORLD
+    world = min(n_gpu, 8)   # dist.PEER_DEFAULT_MAX_WORLD: every GPU of one box
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() % 2000)

@@ -6,7 +6,7 @@ for spec in "$@"; do
   IFS='|' read -r name envs lib <<< "$spec"
   libenv=""
   [ "$lib" != "-" ] && [ -n "$lib" ] && libenv="DRT_B200_LIB=$PWD/drt_b200/_C/variants/lib_$lib.so"
-  env $envs $libenv python bench.py --steps ${STEPS:-10} --warmup 3 --no-e2e --no-cpu-baseline --no-ref-chain-gpu ${BENCH_ARGS} > gpurun_out/${tag}_$name.json 2> gpurun_out/${tag}_$name.err
+  env $envs $libenv python bench.py --steps ${STEPS:-10} --warmup 3 --no-e2e --no-cpu-baseline --no-ref-chain-gpu --no-iteration ${BENCH_ARGS} > gpurun_out/${tag}_$name.json 2> gpurun_out/${tag}_$name.err
   python - <<PY
 import json
 try:
