@@ -152,8 +152,8 @@ struct drt_bvh {
     int4* listA = nullptr;     size_t capLA = 0; // wavefront list L (ray, tri1, tri2, dead) of the rays that hit
     int4* listB = nullptr;     size_t capLB = 0; // wavefront list M: entries of L that survive both refractions
     double* park = nullptr;    size_t capPk = 0; // loss step: parked rays, 6 component columns of capPk/6 slots
-    int* listM = nullptr;      size_t capLM = 0; // loss step: slots of L that survive both refractions
-    int* listS = nullptr;      size_t capLS = 0; // loss step: slots of L whose exit ray is unoccluded (the valid paths)
+    int2* listM = nullptr;     size_t capLM = 0; // loss step: (slot of L, target slot) of the rays that survive both refractions
+    int4* listS = nullptr;     size_t capLS = 0; // loss step: (ray, tri1, tri2, target slot) of the valid paths; before Q1: the beam pass's tile list
     int* tbucket = nullptr;    size_t capTb = 0; // loss step: bucket table of the sparse screen targets
     unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
     unsigned long long* last_ctl = nullptr;      // control block of the latest drt_ray_loss_step (drt_bvh_last_counts)
@@ -731,8 +731,8 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
     ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park);
     LossExitJob j2{park, b->listA};
     DRT_LAUNCH_Q(ls_q2_kernel, b->view(), j2, countL, ctl + 1, pol[1]);
-    ls_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, b->listA, countL, park, b->listM, countM);
-    LossOcclusionJob j3{park, b->listM, b->listS, countS};
+    ls_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, b->listA, countL, park, tgt, b->listM, countM);
+    LossOcclusionJob j3{park, b->listM, b->listA, b->listS, countS};
     DRT_LAUNCH_Q(ls_q3_kernel, b->view(), j3, countM, ctl + 2, pol[2]);
 #undef DRT_LAUNCH_Q
     if (ev_after_fwd) CU(cudaEventRecord((cudaEvent_t)ev_after_fwd, st));
@@ -740,11 +740,11 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
     // grid = what is co-resident (the kernel is register-bound at 3-4 blocks per SM): a larger grid-stride grid only adds a ragged last wave
     const int bgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * std::max(1, grad_V ? (merge ? b->bwd_blocks[2] : b->bwd_blocks[1]) : b->bwd_blocks[0]));
     if (!grad_V)
-        ls_loss_bwd_kernel<false, false><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, nullptr);
+        ls_loss_bwd_kernel<false, false><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listS, countS, tgt, loss_sum, nullptr);
     else if (merge)
-        ls_loss_bwd_kernel<true, true><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
+        ls_loss_bwd_kernel<true, true><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listS, countS, tgt, loss_sum, grad_V);
     else
-        ls_loss_bwd_kernel<true, false><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, b->listS, countS, tgt, loss_sum, grad_V);
+        ls_loss_bwd_kernel<true, false><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listS, countS, tgt, loss_sum, grad_V);
     g_launches += 6;
     CU(cudaGetLastError());
     if (n_paths) CU(cudaMemcpyAsync(n_paths, countS, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));

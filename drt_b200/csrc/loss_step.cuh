@@ -47,6 +47,20 @@ struct TargetSrc {
     const int* __restrict__ bucket;  // [(N >> kTgtShift) + 2]
     int n_tgt;
     int sparse;
+    // slot of ray i's target (sparse: position in idx/xyz; dense: the ray index itself), -1 when the ray has none
+    __device__ __forceinline__ int find(int i) const
+    {
+        if (sparse) {
+            int lo = __ldg(bucket + (i >> kTgtShift)), hi = __ldg(bucket + (i >> kTgtShift) + 1);  // lower_bound in [lo, hi)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(idx + mid) < i) lo = mid + 1; else hi = mid;
+            }
+            return (lo < n_tgt && __ldg(idx + lo) == i) ? lo : -1;
+        }
+        return (valid && !valid[i]) ? -1 : i;
+    }
+    __device__ __forceinline__ d3 point(int slot) const { return ld3((sparse ? xyz : screen) + 3 * (int64_t)slot); }
     __device__ __forceinline__ bool get(int i, d3& s) const
     {
         if (sparse) {
@@ -193,9 +207,12 @@ __global__ void __launch_bounds__(128, MINB) ls_q2_kernel(BvhView B, LossExitJob
 }
 
 // ---- R2: refraction at the exit hit; exit ray parked in place, surviving SLOTS appended to M ---------
+// M entry = (slot in L, slot of the ray's screen target or -1): the target search (a bucket lookup + <= 6 dependent reads) is
+// done HERE, in a dense 32-lane kernel with occupancy to spare, instead of at the head of the register-bound loss/backward
+// kernel, where ncu (r02a) attributed a quarter of its stall samples to that dependent chain.
 __global__ void __launch_bounds__(128) ls_r2_kernel(BvhView B, const double* __restrict__ V64, double ext_ior, double int_ior,
-                                                    const int4* __restrict__ L, const int* __restrict__ countL, Park park,
-                                                    int* __restrict__ M, int* __restrict__ countM)
+                                                    const int4* __restrict__ L, const int* __restrict__ countL, Park park, TargetSrc tgt,
+                                                    int2* __restrict__ M, int* __restrict__ countM)
 {
     const int n = *countL;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -211,7 +228,7 @@ __global__ void __launch_bounds__(128) ls_r2_kernel(BvhView B, const double* __r
             if (alive) park.store(k, o2, d2);
         }
         int slot = warp_append<>(countM, alive);
-        if (slot >= 0) M[slot] = k;
+        if (slot >= 0) M[slot] = make_int2(k, tgt.find(e.x));
     }
 }
 
@@ -221,18 +238,23 @@ struct LossOcclusionJob {
     __device__ __forceinline__ bool bulk_miss(int, unsigned) { return false; }
     __device__ __forceinline__ void finish(unsigned) {}
     Park park;
-    const int* __restrict__ M;
-    int* __restrict__ S;
+    const int2* __restrict__ M;
+    const int4* __restrict__ L;
+    int4* __restrict__ S;  // valid paths: (ray, tri1, tri2, target slot) -- everything the loss/backward kernel needs, one load
     int* __restrict__ countS;
     __device__ __forceinline__ bool load(int m, d3& o, d3& d) const
     {
-        park.load(M[m], o, d);
+        park.load(M[m].x, o, d);
         return true;
     }
     __device__ __forceinline__ void retire(int m, int id, double) const
     {
         int slot = warp_append<>(countS, id < 0);
-        if (slot >= 0) S[slot] = M[m];
+        if (slot >= 0) {
+            const int2 e = M[m];
+            const int4 l = L[e.x];
+            S[slot] = make_int4(l.x, l.y, l.z, e.y);
+        }
     }
 };
 
@@ -251,8 +273,8 @@ __global__ void __launch_bounds__(128, MINB) ls_q3_kernel(BvhView B, LossOcclusi
 // of the chain (common.cuh:hit_backward) into grad_V.  GRAD = false: loss value only.
 template <bool GRAD, bool MERGE>
 __global__ void __launch_bounds__(128, DRT_BWD_MINB) ls_loss_bwd_kernel(BvhView B, const double* __restrict__ V64, RaySrc rays,
-                                                             double ext_ior, double int_ior, const int4* __restrict__ L,
-                                                             const int* __restrict__ S, const int* __restrict__ countS,
+                                                             double ext_ior, double int_ior,
+                                                             const int4* __restrict__ S, const int* __restrict__ countS,
                                                              TargetSrc tgt, double* __restrict__ loss_sum,
                                                              double* __restrict__ gV)
 {
@@ -265,10 +287,10 @@ __global__ void __launch_bounds__(128, DRT_BWD_MINB) ls_loss_bwd_kernel(BvhView 
         d3 z = mk3(0, 0, 0);
         d3 g1[3] = {z, z, z}, g2[3] = {z, z, z};
         if (s < n) {
-            const int4 e = L[S[s]];
+            const int4 e = __ldg(S + s);  // (ray, tri1, tri2, target slot)
             const int i = e.x;
-            d3 sp;
-            if (tgt.get(i, sp)) {
+            if (e.w >= 0) {
+                const d3 sp = tgt.point(e.w);
                 const d3 o = rays.o(i), d = rays.d(i);
                 d3 a0, a1, a2, o1, d1, o2, d2, go1, gd1, go0, gd0;
                 {
