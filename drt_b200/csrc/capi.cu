@@ -68,6 +68,9 @@ struct Tuning {
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
     bool coop_build = false;  // DRT_COOP_BUILD=1: the LBVH build as ONE cooperative launch (bvh_coop.cuh) -- measured SLOWER on B200 (0.208 vs 0.170 ms at 50 k triangles: 15 grid-wide barriers at ~5 us each and L2-only reads cost more than 18 launch boundaries), kept as a tested option
     bool beam = true;  // DRT_BEAM=0: entry query without beam culling of whole pixel tiles (A/B switch)
+    int lanes = 2;  // DRT_LANES=1: drt_ray_loss_step on the caller's stream only (no split); =2..4 forces that many lanes at any size
+    bool lanes_forced = false;
+    int64_t lanes_max_rays = 16 << 20;  // default: two lanes for batches up to 16 M rays
     int beam_steps = 1 << 30;  // DRT_BEAM_STEPS: node steps after which an undecided beam is kept
     int beam_tpb = 0;  // DRT_BEAM_TPB = 1..32 forces the tiles a warp takes per work fetch (default: by batch size)
     int thresh = 32;
@@ -112,6 +115,8 @@ struct Tuning {
         if (cb && !strcmp(cb, "1")) coop_build = true;
         const char* bm2 = getenv("DRT_BEAM");
         if (bm2 && !strcmp(bm2, "0")) beam = false;
+        const char* ln = getenv("DRT_LANES");
+        if (ln && atoi(ln) >= 1 && atoi(ln) <= 4) { lanes = atoi(ln); lanes_forced = lanes >= 2; }
         const char* bs = getenv("DRT_BEAM_STEPS");
         if (bs && atoi(bs) >= 1) beam_steps = atoi(bs);
         const char* tp = getenv("DRT_BEAM_TPB");
@@ -156,7 +161,9 @@ struct drt_bvh {
     int4* listS = nullptr;     size_t capLS = 0; // loss step: (ray, tri1, tri2, target slot) of the valid paths; before Q1: the beam pass's tile list
     int* tbucket = nullptr;    size_t capTb = 0; // loss step: bucket table of the sparse screen targets
     unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
-    unsigned long long* last_ctl = nullptr;      // control block of the latest drt_ray_loss_step (drt_bvh_last_counts)
+    cudaStream_t lane_stream[4] = {};            // internal streams of the lanes of drt_ray_loss_step
+    cudaEvent_t lane_event[9] = {};              // fork, forward done x4, done x4
+    unsigned long long* last_ctl[4] = {};        // control blocks (one per lane) of the latest drt_ray_loss_step (drt_bvh_last_counts)
     int64_t last_tiles = 0;                      // its number of 32-ray tiles (0: no beam pass)
     int work_slot = 0;
     int build_blocks_per_sm = 0;                 // co-resident blocks of lbvh_build_kernel (0: no cooperative launch)
@@ -222,6 +229,13 @@ int beam_tiles_per_fetch(int64_t N, int warps)
     int tpb = 32;
     while (tpb > 4 && tiles / tpb < (int64_t)warps * 4) tpb >>= 1;
     return tpb;
+}
+
+constexpr int kMaxLanes = 4;
+
+__global__ void sum_counts_kernel(const int* a, const int* b, const int* c, const int* d, int32_t* out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = *a + (b ? *b : 0) + (c ? *c : 0) + (d ? *d : 0);
 }
 
 // clamp + count out-of-range indices so that no later kernel can fault on a bad face list
@@ -407,6 +421,8 @@ int drt_bvh_create(int device, drt_bvh** out)
         if (coop) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->fused6_blocks_per_sm, wf_fused_kernel<6>, 128, 0));
     }
 
+    for (int k = 0; k < 4; ++k) CU(cudaStreamCreateWithFlags(&b->lane_stream[k], cudaStreamNonBlocking));
+    for (int k = 0; k < 9; ++k) CU(cudaEventCreateWithFlags(&b->lane_event[k], cudaEventDisableTiming));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[0], ls_loss_bwd_kernel<false, false>, 128, 0));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[1], ls_loss_bwd_kernel<true, false>, 128, 0));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[2], ls_loss_bwd_kernel<true, true>, 128, 0));
@@ -422,6 +438,10 @@ int drt_bvh_destroy(drt_bvh* b)
     void* ptrs[] = {b->listA, b->listB, b->park, b->listM, b->listS, b->tbucket, b->work, b->F, b->V32, b->keys, b->sort_table, b->children, b->parent, b->blo, b->bhi, b->flags, b->scene, b->nodes, b->nodes4, b->tris};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (cudaStream_t q : b->lane_stream)
+        if (q) cudaStreamDestroy(q);
+    for (cudaEvent_t e : b->lane_event)
+        if (e) cudaEventDestroy(e);
     delete b;
     return DRT_OK;
 }
@@ -486,14 +506,18 @@ int drt_bvh_last_counts(const drt_bvh* b, void* stream, int64_t out[6])
 {
     if (!b || !out) return fail(DRT_ERR_INVALID, "drt_bvh_last_counts: null argument");
     for (int k = 0; k < 6; ++k) out[k] = 0;
-    if (!b->last_ctl) return DRT_OK;
+    if (!b->last_ctl[0]) return DRT_OK;
     DeviceGuard g(b->device);
-    unsigned long long h[8];
-    CU(cudaMemcpyAsync(h, b->last_ctl, sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    unsigned long long h[4][8] = {};
+    for (int k = 0; k < 4; ++k)
+        if (b->last_ctl[k]) CU(cudaMemcpyAsync(h[k], b->last_ctl[k], sizeof h[k], cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    const int* c = reinterpret_cast<const int*>(h);
-    out[0] = c[6]; out[1] = c[7]; out[2] = c[8];   // entry hits, survivors of both refractions, valid paths
-    out[3] = b->last_tiles; out[4] = b->last_tiles ? c[10] : 0;  // tiles seen / kept by the beam pass
+    for (int k = 0; k < 4; ++k) {
+        const int* c = reinterpret_cast<const int*>(h[k]);
+        out[0] += c[6]; out[1] += c[7]; out[2] += c[8];   // entry hits, survivors of both refractions, valid paths
+        out[4] += b->last_tiles ? c[10] : 0;              // tiles kept by the beam pass
+    }
+    out[3] = b->last_tiles;
     return DRT_OK;
 }
 
@@ -685,20 +709,9 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
     if ((rc = ensure(b->park, b->capPk, 6 * (size_t)N))) return rc;
     if ((rc = ensure(b->listM, b->capLM, (size_t)N))) return rc;
     if ((rc = ensure(b->listS, b->capLS, (size_t)N))) return rc;  // also holds the int2 list of surviving tiles (N/16 ints) before Q3
-    // control block: work counters of Q1,Q2,Q3 + {countL, countM} + {countS, -}
-    unsigned long long* ctl = b->work + (size_t)(b->work_slot++ % (kWorkSlots / 8)) * 8;
-    CU(cudaMemsetAsync(ctl, 0, 8 * sizeof(unsigned long long), st));
-    int* countL = (int*)(ctl + 3);
-    int* countM = countL + 1;
-    int* countS = (int*)(ctl + 4);
-    b->last_ctl = ctl;
-    b->last_tiles = 0;
     const int* pol = tuning().pol;
     const int minb = tuning().minb;
-    const int dgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * tuning().r_grid);
-    const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
     const RaySrc rays{origin, dir, (int)rays_per_origin};
-    const Park park{b->park, (int64_t)(b->capPk / 6)};
     const int n_buckets = (int)(N >> kTgtShift) + 2;
     if (target_mode == 1) {
         if ((rc = ensure(b->tbucket, b->capTb, (size_t)n_buckets))) return rc;
@@ -706,48 +719,142 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
         ++g_launches;
     }
     const TargetSrc tgt{screen, valid, tgt_idx, tgt_xyz, b->tbucket, (int)n_tgt, target_mode};
-#define DRT_LAUNCH_Q(KERNEL, ...)                                                           \
-    do {                                                                                    \
-        if (minb == 10) KERNEL<10><<<pg, 128, 0, st>>>(__VA_ARGS__);                        \
-        else if (minb == 8) KERNEL<8><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
-        else if (minb == 7) KERNEL<7><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
-        else if (minb == 6) KERNEL<6><<<pg, 128, 0, st>>>(__VA_ARGS__);                     \
-        else KERNEL<4><<<pg, 128, 0, st>>>(__VA_ARGS__);                                    \
-    } while (0)
-    // whole images of image_w x image_h pixels that a 32-pixel tile shape divides: a warp's batch becomes a pixel tile
-    LossEntryJob j1{rays, b->listA, countL, tile_map(image_w, image_h, N, false)};
-#if DRT_QNODE
-    if (tuning().beam && (pol[0] & 0xff) == 32) {
-        // beam pass over all tiles -> list of the surviving tiles (in listS, free until Q3) -> per-ray entry query over the list
-        int2* tiles = reinterpret_cast<int2*>(b->listS);
-        int* n_tiles = (int*)(ctl + 5);
-        b->last_tiles = (N + 31) / 32;
-        ls_beam_kernel<<<pg, 128, 0, st>>>(b->view(), j1, (int)N, ctl + 0, beam_tiles_per_fetch(N, pg * 4), tuning().beam_steps, tiles, n_tiles);
-        ++g_launches;
-        DRT_LAUNCH_Q(ls_q1_tiles_kernel, b->view(), j1, (int)N, tiles, n_tiles, ctl + 6, pol[0]);
-    } else
-#endif
-    DRT_LAUNCH_Q(ls_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
-    ls_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listA, countL, park);
-    LossExitJob j2{park, b->listA};
-    DRT_LAUNCH_Q(ls_q2_kernel, b->view(), j2, countL, ctl + 1, pol[1]);
-    ls_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, b->listA, countL, park, tgt, b->listM, countM);
-    LossOcclusionJob j3{park, b->listM, b->listA, b->listS, countS};
-    DRT_LAUNCH_Q(ls_q3_kernel, b->view(), j3, countM, ctl + 2, pol[2]);
-#undef DRT_LAUNCH_Q
-    if (ev_after_fwd) CU(cudaEventRecord((cudaEvent_t)ev_after_fwd, st));
     const bool merge = tuning().bwd_merge == 1 || (tuning().bwd_merge < 0 && N / std::max(b->nV, 1) > kMergeRaysPerVertex);
-    // grid = what is co-resident (the kernel is register-bound at 3-4 blocks per SM): a larger grid-stride grid only adds a ragged last wave
-    const int bgrid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * std::max(1, grad_V ? (merge ? b->bwd_blocks[2] : b->bwd_blocks[1]) : b->bwd_blocks[0]));
-    if (!grad_V)
-        ls_loss_bwd_kernel<false, false><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listS, countS, tgt, loss_sum, nullptr);
-    else if (merge)
-        ls_loss_bwd_kernel<true, true><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listS, countS, tgt, loss_sum, grad_V);
-    else
-        ls_loss_bwd_kernel<true, false><<<bgrid, 128, 0, st>>>(b->view(), V64, rays, ext_ior, int_ior, b->listS, countS, tgt, loss_sum, grad_V);
-    g_launches += 6;
+
+    // Two LANES: the batch is split in two halves (at an image boundary when the image size is known) that run the same seven
+    // stages on two internal streams with their own halves of the scratch.  Every stage is a persistent kernel that ends in a
+    // tail of a few long rays while most SMs idle; with two lanes the other half's kernels fill those tails (the block scheduler
+    // starts them as the blocks of the draining kernel exit).  Results do not depend on it (the halves only share the atomically
+    // accumulated loss and gradient).  DRT_LANES=1 switches it off.
+    const int64_t img = (image_w > 0 && image_h > 0) ? (int64_t)image_w * image_h : 0;
+    // measured on B200 (C4): 9 views (6.2 M rays) 1.32 -> 1.27 ms with two lanes, 72 views (49.8 M rays) 5.77 -> 5.85 ms: the
+    // tails only matter when a stage lasts a few hundred microseconds, so large batches stay on one lane
+    int n_lanes = 1;
+    int64_t cut[kMaxLanes + 1] = {0, N, N, N, N};  // lane k = rays [cut[k], cut[k+1])
+    if (tuning().lanes >= 2 && b->lane_stream[0] && N >= (1 << 17) && (N <= tuning().lanes_max_rays || tuning().lanes_forced)) {
+        const int64_t unit = (img > 0 && N % img == 0) ? img : (img == 0 ? 32 : 0);  // split at image boundaries (else at 32-ray batches)
+        if (unit > 0) {
+            const int64_t units = N / unit;
+            n_lanes = (int)std::min<int64_t>(tuning().lanes, std::max<int64_t>(1, units));
+            for (int k = 1; k < n_lanes; ++k) cut[k] = (units * k / n_lanes) * unit;
+            for (int k = n_lanes; k <= kMaxLanes; ++k) cut[k] = N;
+            for (int k = 0; k < n_lanes; ++k)
+                if (cut[k + 1] <= cut[k]) { n_lanes = 1; cut[1] = N; break; }  // degenerate split: one lane
+        }
+    }
+    cudaStream_t ls[kMaxLanes] = {st, st, st, st};
+    if (n_lanes > 1) {
+        CU(cudaEventRecord(b->lane_event[0], st));  // fork: the lanes start after everything enqueued on the caller's stream
+        for (int k = 0; k < n_lanes; ++k) {
+            ls[k] = b->lane_stream[k];
+            CU(cudaStreamWaitEvent(ls[k], b->lane_event[0], 0));
+        }
+    }
+    struct Lane {
+        int64_t base, n;
+        unsigned long long* ctl;
+        int *countL, *countM, *countS;
+        int4* L;
+        int2* M;
+        int4* S;
+        Park park;
+        int pg, dgrid;
+    } lane[kMaxLanes];
+    const int64_t capL = (int64_t)b->capLA, capM = (int64_t)b->capLM, capS = (int64_t)b->capLS, capP = (int64_t)(b->capPk / 6);
+    for (int k = 0; k < n_lanes; ++k) {
+        Lane& l = lane[k];
+        l.base = cut[k];
+        l.n = cut[k + 1] - cut[k];
+        // control block: work counters of Q1,Q2,Q3 + {countL, countM} + {countS, -} + {tiles kept, -} + tile-list work counter
+        l.ctl = b->work + (size_t)(b->work_slot++ % (kWorkSlots / 8)) * 8;
+        CU(cudaMemsetAsync(l.ctl, 0, 8 * sizeof(unsigned long long), ls[k]));
+        l.countL = (int*)(l.ctl + 3);
+        l.countM = l.countL + 1;
+        l.countS = (int*)(l.ctl + 4);
+        // each lane owns the part of the scratch that corresponds to its share of the rays (capacities are >= N entries)
+        l.L = b->listA + (int64_t)((__int128)capL * cut[k] / N);
+        l.M = b->listM + (int64_t)((__int128)capM * cut[k] / N);
+        l.S = b->listS + (int64_t)((__int128)capS * cut[k] / N);
+        l.park = Park{b->park + (int64_t)((__int128)capP * cut[k] / N), capP};
+        l.pg = (int)std::min<int64_t>(blocks_for(l.n, 128), (int64_t)b->sm_count * minb);
+        l.dgrid = (int)std::min<int64_t>(blocks_for(l.n, 128), (int64_t)b->sm_count * tuning().r_grid);
+    }
+    for (int k = 0; k < kMaxLanes; ++k) b->last_ctl[k] = k < n_lanes ? lane[k].ctl : nullptr;
+    b->last_tiles = 0;
+#define DRT_LAUNCH_Q(KERNEL, PG, ST, ...)                                                   \
+    do {                                                                                    \
+        if (minb == 10) KERNEL<10><<<PG, 128, 0, ST>>>(__VA_ARGS__);                        \
+        else if (minb == 8) KERNEL<8><<<PG, 128, 0, ST>>>(__VA_ARGS__);                     \
+        else if (minb == 7) KERNEL<7><<<PG, 128, 0, ST>>>(__VA_ARGS__);                     \
+        else if (minb == 6) KERNEL<6><<<PG, 128, 0, ST>>>(__VA_ARGS__);                     \
+        else KERNEL<4><<<PG, 128, 0, ST>>>(__VA_ARGS__);                                    \
+    } while (0)
+    const bool beam = DRT_QNODE && tuning().beam && (pol[0] & 0xff) == 32;
+    // stage by stage, lane by lane: the launches of the two lanes alternate so that neither stream waits for the host
+    for (int k = 0; k < n_lanes; ++k) {  // Q1: entry query
+        Lane& l = lane[k];
+        // whole images of image_w x image_h pixels that a 32-pixel tile shape divides: a warp's batch becomes a pixel tile
+        LossEntryJob j1{rays, l.L, l.countL, tile_map(image_w, image_h, l.n, false), (int)l.base};
+        if (l.base % 32 != 0 || (j1.tiles.img_w && l.base % j1.tiles.img_hw != 0)) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: internal lane split is not tile aligned");
+#if DRT_QNODE
+        if (beam) {
+            // beam pass over all tiles -> list of the surviving tiles (in the lane's part of listS, free until Q3) -> per-ray
+            // entry query over the list
+            int2* tiles = reinterpret_cast<int2*>(l.S);
+            int* n_tiles = (int*)(l.ctl + 5);
+            b->last_tiles += (l.n + 31) / 32;
+            // one beam per LANE needs 32 tiles per fetch: small batches get a smaller grid (>= 2 fetches per warp), not fewer tiles
+            const int tpb = tuning().beam_tpb ? tuning().beam_tpb : 32;
+            const int bg = (int)std::max<int64_t>(1, std::min<int64_t>(l.pg, ((l.n + 31) / 32 + (int64_t)tpb * 8 - 1) / ((int64_t)tpb * 8)));
+            ls_beam_kernel<<<bg, 128, 0, ls[k]>>>(b->view(), j1, (int)l.n, l.ctl + 0, tpb, tuning().beam_steps, tiles, n_tiles);
+            ++g_launches;
+            DRT_LAUNCH_Q(ls_q1_tiles_kernel, l.pg, ls[k], b->view(), j1, (int)l.n, tiles, n_tiles, l.ctl + 6, pol[0]);
+        } else
+#endif
+        DRT_LAUNCH_Q(ls_q1_kernel, l.pg, ls[k], b->view(), j1, (int)l.n, l.ctl + 0, pol[0]);
+    }
+    for (int k = 0; k < n_lanes; ++k) {  // R1 + Q2: refraction at the entry hit, exit query
+        Lane& l = lane[k];
+        ls_r1_kernel<<<l.dgrid, 128, 0, ls[k]>>>(b->view(), V64, rays, ext_ior, int_ior, l.L, l.countL, l.park);
+        LossExitJob j2{l.park, l.L};
+        DRT_LAUNCH_Q(ls_q2_kernel, l.pg, ls[k], b->view(), j2, l.countL, l.ctl + 1, pol[1]);
+    }
+    for (int k = 0; k < n_lanes; ++k) {  // R2 + Q3: refraction at the exit hit (+ target lookup), occlusion query
+        Lane& l = lane[k];
+        ls_r2_kernel<<<l.dgrid, 128, 0, ls[k]>>>(b->view(), V64, ext_ior, int_ior, l.L, l.countL, l.park, tgt, l.M, l.countM);
+        LossOcclusionJob j3{l.park, l.M, l.L, l.S, l.countS};
+        DRT_LAUNCH_Q(ls_q3_kernel, l.pg, ls[k], b->view(), j3, l.countM, l.ctl + 2, pol[2]);
+    }
+#undef DRT_LAUNCH_Q
+    if (ev_after_fwd) {
+        for (int k = 0; k < n_lanes && n_lanes > 1; ++k) {  // the marker fires when ALL lanes have finished their forward part
+            CU(cudaEventRecord(b->lane_event[1 + k], ls[k]));
+            CU(cudaStreamWaitEvent(st, b->lane_event[1 + k], 0));
+        }
+        CU(cudaEventRecord((cudaEvent_t)ev_after_fwd, st));
+    }
+    for (int k = 0; k < n_lanes; ++k) {  // loss + backward over the valid paths
+        Lane& l = lane[k];
+        // grid = what is co-resident (the kernel is register-bound at 3-4 blocks per SM): a larger grid-stride grid only adds a ragged last wave
+        const int bgrid = (int)std::min<int64_t>(blocks_for(l.n, 128), (int64_t)b->sm_count * std::max(1, grad_V ? (merge ? b->bwd_blocks[2] : b->bwd_blocks[1]) : b->bwd_blocks[0]));
+        if (!grad_V)
+            ls_loss_bwd_kernel<false, false><<<bgrid, 128, 0, ls[k]>>>(b->view(), V64, rays, ext_ior, int_ior, l.S, l.countS, tgt, loss_sum, nullptr);
+        else if (merge)
+            ls_loss_bwd_kernel<true, true><<<bgrid, 128, 0, ls[k]>>>(b->view(), V64, rays, ext_ior, int_ior, l.S, l.countS, tgt, loss_sum, grad_V);
+        else
+            ls_loss_bwd_kernel<true, false><<<bgrid, 128, 0, ls[k]>>>(b->view(), V64, rays, ext_ior, int_ior, l.S, l.countS, tgt, loss_sum, grad_V);
+    }
+    g_launches += 6 * n_lanes;
     CU(cudaGetLastError());
-    if (n_paths) CU(cudaMemcpyAsync(n_paths, countS, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    for (int k = 0; k < n_lanes && n_lanes > 1; ++k) {  // join: the caller's stream continues after all lanes
+        CU(cudaEventRecord(b->lane_event[1 + kMaxLanes + k], ls[k]));
+        CU(cudaStreamWaitEvent(st, b->lane_event[1 + kMaxLanes + k], 0));
+    }
+    if (n_paths) {
+        sum_counts_kernel<<<1, 32, 0, st>>>(lane[0].countS, n_lanes > 1 ? lane[1].countS : nullptr, n_lanes > 2 ? lane[2].countS : nullptr,
+                                            n_lanes > 3 ? lane[3].countS : nullptr, n_paths);
+        ++g_launches;
+    }
     return DRT_OK;
 }
 

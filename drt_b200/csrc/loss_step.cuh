@@ -121,7 +121,8 @@ struct LossEntryJob {
     int4* __restrict__ L;
     int* __restrict__ countL;
     TileMap tiles;
-    __device__ __forceinline__ int ray_of(int item) const { return tiles.ray_of(item); }
+    int base;  // first ray of this launch's share of the batch (drt_ray_loss_step may split a batch over two streams)
+    __device__ __forceinline__ int ray_of(int item) const { return tiles.ray_of(item + base); }
     __device__ __forceinline__ bool load(int item, d3& o, d3& d) const
     {
         load_ray(ray_of(item), o, d);

@@ -159,7 +159,7 @@ __device__ __forceinline__ void beam_pass(const BvhView& B, Job& job, int total,
         if ((int)lane < tpb) {
             const int first = base + 32 * (int)lane;
             // the 32 work items of a tile map to rays r0 + row * img_w + col (TileMap): one index computation per tile, not per ray
-            const int r0 = job.tiles.ray_of(first);
+            const int r0 = job.ray_of(first);
             const int tw_log2 = job.tiles.tw_log2, tw_mask = (1 << tw_log2) - 1, row_stride = job.tiles.img_w;
             // rays that provably read the same origin row (one row per view, captured_data.py:38) need it once per tile
             const int r_last = row_stride ? r0 + (31 >> tw_log2) * row_stride + tw_mask : r0 + 31;
@@ -274,6 +274,7 @@ struct EntryJob {
     int4* __restrict__ L;
     int* __restrict__ countL;
     TileMap tiles;  // work item -> ray (8 x 4 pixel tiles when the image size is known)
+    __device__ __forceinline__ int ray_of(int item) const { return tiles.ray_of(item); }
     __device__ __forceinline__ bool load(int item, d3& o, d3& d) const
     {
         load_ray(tiles.ray_of(item), o, d);
