@@ -558,6 +558,13 @@ def run_b200(args):
     if args.loss_path == "step":  # marks[2] = end of the forward wavefront (recorded by the library), marks[4] = end of backward
         phases[3] = phases[2] + phases[3]
         phases[2] = 0.0
+    # every rank's own compute time per step (everything before the all-reduce): their spread IS the arrival skew
+    my_compute = sum(m[0].elapsed_time(m[4]) for m in marks) / args.steps
+    rank_compute = [my_compute]
+    if world > 1:
+        g_all = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(g_all, torch.tensor([my_compute], dtype=torch.float64, device=dev))
+        rank_compute = [float(x.item()) for x in g_all]
     tt = torch.tensor([t_total_ms, phases[1], phases[3], phases[0], phases[4]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -593,6 +600,24 @@ def run_b200(args):
                     "ranks_bit_identical": bool(cmin.item() == cmax.item()), "ok": bool(rel.item() <= 1e-12 and cmin.item() == cmax.item())}
         if not ar_check["ok"]:
             raise SystemExit("bench.py: all-reduce self-check failed: " + json.dumps(ar_check))
+        # latency of the collective alone (ranks aligned by a barrier, 50 back-to-back calls): what the all-reduce PHASE of a
+        # step exceeds this by is the ranks' arrival skew, not the collective
+        lat = {}
+        for name, fn in (("used_by_the_step", lambda t: ddist.allreduce_grad(t)), ("torch_distributed_nccl", lambda t: dist.all_reduce(t))):
+            fn(a)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(50):
+                fn(a)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([e0.elapsed_time(e1) / 50 * 1e3], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lat[name] = float(t.item())
+        ar_check["latency_us"] = lat
     sync_all()
 
     # ---- e2e: host buffers, copies inside the timed region ----------------------------------
@@ -946,7 +971,7 @@ def run_b200(args):
                                     if cpu and (e2e or e2e_ref_layout) else None),
             "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "optim_iteration": optim_iter, "e2e": e2e, "e2e_reference_layout": e2e_ref_layout, "e2e_pinhole": e2e_pinhole, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "loss": loss_val, "grad_norm": grad_norm,
-            "stage_counts_rank0": stage_counts, "parity_check": parity, "allreduce_check": ar_check, "shard": {"policy": args.shard if world > 1 else "none", "skew": shard_skew}, "numa_rank0": numa,
+            "stage_counts_rank0": stage_counts, "parity_check": parity, "allreduce_check": ar_check, "shard": {"policy": args.shard if world > 1 else "none", "skew": shard_skew, "rank_compute_ms": rank_compute}, "numa_rank0": numa,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

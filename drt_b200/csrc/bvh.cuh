@@ -160,8 +160,10 @@ __device__ __forceinline__ uint64_t spread13(uint32_t v)
     return x;
 }
 
+// hist != nullptr: also accumulate the first sort pass's per-tile digit histogram (radix_sort.cuh), table cleared by the caller
 __global__ void morton_kernel(const int32_t* __restrict__ F, const float* __restrict__ V, int nF,
-                              const unsigned* __restrict__ scene, uint64_t* __restrict__ keys)
+                              const unsigned* __restrict__ scene, uint64_t* __restrict__ keys, unsigned* __restrict__ hist, int hist_shift,
+                              int hist_tiles)
 {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nF) return;
@@ -178,7 +180,9 @@ __global__ void morton_kernel(const int32_t* __restrict__ F, const float* __rest
         q[k] = (uint32_t)s;
     }
     uint64_t morton = (spread13(q[0]) << 2) | (spread13(q[1]) << 1) | spread13(q[2]);
-    keys[f] = (morton << kIndexBits) | (uint64_t)(uint32_t)f;
+    const uint64_t key = (morton << kIndexBits) | (uint64_t)(uint32_t)f;
+    keys[f] = key;
+    if (hist) atomicAdd(&hist[((unsigned)(key >> hist_shift) & 255u) * hist_tiles + f / kSortTile], 1u);
 }
 
 __device__ __forceinline__ int key_tri(uint64_t key) { return (int)(key & ((1ull << kIndexBits) - 1)); }

@@ -307,7 +307,7 @@ int build_tree(drt_bvh* b, cudaStream_t st, const double* pending_V64 = nullptr)
     }
     int rc;
     if ((rc = ensure(b->keys, b->capK, 2 * (size_t)n))) return rc;
-    if ((rc = ensure(b->sort_table, b->capSt, 256 * (size_t)sort_tiles(n)))) return rc;
+    if ((rc = ensure(b->sort_table, b->capSt, sort_table_words(n, kIndexBits)))) return rc;
     if ((rc = ensure(b->children, b->capCh, (size_t)n))) return rc;
     if ((rc = ensure(b->parent, b->capP, 2 * (size_t)n))) return rc;
     if ((rc = ensure(b->blo, b->capBl, 2 * (size_t)n))) return rc;
@@ -325,10 +325,11 @@ int build_tree(drt_bvh* b, cudaStream_t st, const double* pending_V64 = nullptr)
     }
 
     init_scene_kernel<<<1, 32, 0, st>>>(b->scene, false); ++g_launches;
+    CU(cudaMemsetAsync(b->sort_table, 0, sort_table_words(n, kIndexBits) * sizeof(unsigned), st));  // the digit tables of all sort passes
     centroid_bounds_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene); ++g_launches;
-    morton_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene, b->keys); ++g_launches;
-    // unique keys (Morton << 25 | id): keys-only LSD radix sort over the Morton bits
-    b->sorted_keys = sort_keys_u64(b->keys, n, kIndexBits, b->sort_table, st, &g_launches);
+    morton_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, n, b->scene, b->keys, b->sort_table, kIndexBits & ~7, sort_tiles(n)); ++g_launches;
+    // unique keys (Morton << 25 | id): keys-only LSD radix sort over the Morton bits, one launch per pass
+    b->sorted_keys = sort_keys_u64(b->keys, n, kIndexBits, b->sort_table, true, st, &g_launches);
     if (n > 1) {
         topology_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>(b->sorted_keys, n, b->children, b->parent);
         ++g_launches;
