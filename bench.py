@@ -64,6 +64,7 @@ def parse():
                          "per step (launch-bound regime: one view per iteration, or 8 GPUs)")
     ap.add_argument("--no-iteration", action="store_true", help="skip the supplementary whole-optim.py-iteration timing")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle check of one view of the timed workload")
+    ap.add_argument("--rebalance", type=int, default=3, help="rounds of measured-cost refinement of the balanced view assignment (N > 1)")
     ap.add_argument("--shard", default="balanced", choices=["balanced", "roundrobin"],
                     help="views -> ranks: by estimated cost (measured pixels per view, LPT) or k mod N")
     return ap.parse_args()
@@ -416,16 +417,19 @@ def run_b200(args):
     nV = V.shape[0]
 
     # ---- synthetic inputs: rays of my views (device + pinned host copies), screen targets ----
-    origin, ray_dir = views.view_batch(cams, resy, resx, device=dev)
     tgt_scene = R.Scene(vertices=configs.perturbed_target_mesh(cfg["vertices"]), faces=cfg["faces"], cuda_device=local)
-    with torch.no_grad():
-        t_ori, t_dir, t_mask = tgt_scene.render_transparent(origin, ray_dir)
-        screen = (t_ori + 100.0 * t_dir).contiguous()      # a measured 3-D screen point per pixel (optim.py:96)
-        valid = t_mask[:, 0].contiguous()
-    del tgt_scene, t_ori, t_dir, t_mask
-    # resident inputs of the fused step: one origin row per view, ray_dir, the measured screen points only
-    origins = torch.stack([origin[j * n_pix] for j in range(len(cams))]) if cams else origin[:0]
-    sparse = losses.SparseTargets.from_dense(screen, valid)
+
+    def make_inputs(cams):
+        origin, ray_dir = views.view_batch(cams, resy, resx, device=dev)
+        with torch.no_grad():
+            t_ori, t_dir, t_mask = tgt_scene.render_transparent(origin, ray_dir)
+            screen = (t_ori + 100.0 * t_dir).contiguous()      # a measured 3-D screen point per pixel (optim.py:96)
+            valid = t_mask[:, 0].contiguous()
+        # resident inputs of the fused step: one origin row per view, ray_dir, the measured screen points only
+        origins = torch.stack([origin[j * n_pix] for j in range(len(cams))]) if cams else origin[:0]
+        return origin, ray_dir, screen, valid, origins, losses.SparseTargets.from_dense(screen, valid)
+
+    origin, ray_dir, screen, valid, origins, sparse = make_inputs(cams)
     g_dir = torch.empty_like(origin) if args.loss_path == "dense" else None
     loss_buf = torch.zeros(1, dtype=torch.float64, device=dev)
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
@@ -479,6 +483,46 @@ def run_b200(args):
         if world > 1:
             ddist.allreduce_grad(V.grad)
     sync_all()
+    # views -> ranks, refined by MEASURED cost: the hit-count estimate balances to 0.05 %, the ranks' real step times still differ
+    # by several per cent (8 GPUs: 0.98 ... 1.07 ms) and the slowest one sets the step.  Each round scales the cost estimate of
+    # every view by its rank's measured / estimated time, reassigns (LPT, identical on every rank) and regenerates the inputs.
+    rebalance_log = []
+    if world > 1 and args.shard == "balanced" and args.loss_path == "step" and args.rebalance > 0:
+        for _round in range(args.rebalance):
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            r0, r1 = ev(), ev()
+            r0.record()
+            for _ in range(5):
+                loss_buf.zero_()
+                step(origin, ray_dir, screen, valid, g_dir)
+            r1.record()
+            torch.cuda.synchronize(dev)
+            g_all = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(g_all, torch.tensor([r0.elapsed_time(r1) / 5], dtype=torch.float64, device=dev))
+            times = [float(x.item()) for x in g_all]
+            assign = [ddist.shard_views_balanced(costs, r, world) for r in range(world)]
+            est = [sum(costs[k] for k in a) for a in assign]
+            norm = sum(est) / sum(times)
+            for r, a in enumerate(assign):
+                for k in a:
+                    costs[k] *= times[r] * norm / est[r]
+            rebalance_log.append({"rank_ms": times, "max_over_mean": max(times) / (sum(times) / world)})
+            new_mine = ddist.shard_views_balanced(costs, rank, world)
+            changed = torch.tensor([int(new_mine != mine)], device=dev)
+            dist.all_reduce(changed, op=dist.ReduceOp.MAX)
+            if not changed.item():
+                break
+            mine = new_mine
+            cams = [cfg["cams"][k] for k in mine]
+            n_local = len(cams) * n_pix
+            del origin, ray_dir, screen, valid, origins, sparse
+            torch.cuda.empty_cache()
+            origin, ray_dir, screen, valid, origins, sparse = make_inputs(cams)
+            for _ in range(2):
+                loss_buf.zero_()
+                step(origin, ray_dir, screen, valid, g_dir)
+        sync_all()
     # The ~30 launches of a step (LBVH rebuild, 8 kernels of the fused ray-loss step, the autograd scale) captured ONCE as a CUDA
     # graph and replayed: same kernels, same arguments (the library's scratch and torch's graph pool are static), no Python or
     # launch overhead between them.  The all-reduce stays outside (its epoch is a kernel argument that changes every call).
@@ -971,7 +1015,8 @@ def run_b200(args):
                                     if cpu and (e2e or e2e_ref_layout) else None),
             "roofline": roof, "cpu_baseline": cpu, "ref_chain_gpu": ref_gpu, "optim_iteration": optim_iter, "e2e": e2e, "e2e_reference_layout": e2e_ref_layout, "e2e_pinhole": e2e_pinhole, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "loss": loss_val, "grad_norm": grad_norm,
-            "stage_counts_rank0": stage_counts, "parity_check": parity, "allreduce_check": ar_check, "shard": {"policy": args.shard if world > 1 else "none", "skew": shard_skew, "rank_compute_ms": rank_compute}, "numa_rank0": numa,
+            "stage_counts_rank0": stage_counts, "parity_check": parity, "allreduce_check": ar_check, "shard": {"policy": args.shard if world > 1 else "none", "skew": shard_skew, "rank_compute_ms": rank_compute,
+                                                                 "measured_rebalance": rebalance_log, "views_per_rank": len(cams)}, "numa_rank0": numa,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

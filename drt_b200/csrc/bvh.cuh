@@ -388,6 +388,74 @@ __global__ void emit_nodes_kernel(int n, const int2* __restrict__ children, cons
 
 #endif  // DRT_QNODE
 
+// Round 2: grid + node + triangle emission as ONE launch (three launches of the 50 k-triangle rebuild's chain less): every thread
+// derives the quantisation grid from the root box itself (same arithmetic as grid_kernel, so the same values), thread 0 publishes
+// it in scene[8..13] for the traversal kernels.
+#if DRT_QNODE
+__global__ void emit_all_kernel(int n, const int32_t* __restrict__ F, const float* __restrict__ V, const uint64_t* __restrict__ keys,
+                                const int2* __restrict__ children, const float4* __restrict__ blo, const float4* __restrict__ bhi,
+                                unsigned* __restrict__ scene, uint4* __restrict__ nodes, uint4* __restrict__ nodes4, double2* __restrict__ tris)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float g0[3], st[3];
+    {
+        const float4 l = blo[0], h = bhi[0];
+        float ext[3] = {__fadd_ru(h.x, -l.x), __fadd_ru(h.y, -l.y), __fadd_ru(h.z, -l.z)};
+        const float lo[3] = {l.x, l.y, l.z};
+        float emax = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
+        if (!(emax > 7.888609052210118e-31f)) emax = 1.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float e = fmaxf(ext[k], emax * 9.5367431640625e-07f);
+            st[k] = __fdiv_ru(e, kGridSteps);
+            g0[k] = __fadd_rd(lo[k], -__fmul_ru(7.f, st[k]));
+        }
+        if (i == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                scene[8 + k] = __float_as_uint(g0[k]);
+                scene[11 + k] = __float_as_uint(st[k]);
+            }
+        }
+    }
+    const float inv_s[3] = {__fdiv_rn(1.f, st[0]), __fdiv_rn(1.f, st[1]), __fdiv_rn(1.f, st[2])};
+    if (n == 1) {
+        if (i == 0) {  // single triangle: both slots are the one leaf (a duplicate test is harmless)
+            float4 l = blo[0], h = bhi[0];
+            const unsigned x = qpair(l.x, h.x, g0[0], inv_s[0]), y = qpair(l.y, h.y, g0[1], inv_s[1]), z = qpair(l.z, h.z, g0[2], inv_s[2]);
+            nodes[0] = make_uint4(x, x, y, y);
+            nodes[1] = make_uint4(z, z, (unsigned)~0, (unsigned)~0);
+            if (nodes4) emit_wide_node(0, n, children, blo, bhi, g0, inv_s, nodes4);
+        }
+    } else if (i < n - 1) {
+        int2 ch = children[i];
+        float4 l0 = blo[ch.x], h0 = bhi[ch.x], l1 = blo[ch.y], h1 = bhi[ch.y];
+        int c0 = ch.x >= n - 1 ? ~(ch.x - (n - 1)) : ch.x;
+        int c1 = ch.y >= n - 1 ? ~(ch.y - (n - 1)) : ch.y;
+        uint4* node = nodes + (size_t)i * kNodeQuads;
+        node[0] = make_uint4(qpair(l0.x, h0.x, g0[0], inv_s[0]), qpair(l1.x, h1.x, g0[0], inv_s[0]), qpair(l0.y, h0.y, g0[1], inv_s[1]),
+                             qpair(l1.y, h1.y, g0[1], inv_s[1]));
+        node[1] = make_uint4(qpair(l0.z, h0.z, g0[2], inv_s[2]), qpair(l1.z, h1.z, g0[2], inv_s[2]), (unsigned)c0, (unsigned)c1);
+        if (nodes4) emit_wide_node(i, n, children, blo, bhi, g0, inv_s, nodes4);
+    }
+    if (i < n) {
+        int f = key_tri(keys[i]);
+        const float* pa = &V[3 * (size_t)F[3 * f]];
+        const float* pb = &V[3 * (size_t)F[3 * f + 1]];
+        const float* pc = &V[3 * (size_t)F[3 * f + 2]];
+        d3 a = mk3((double)pa[0], (double)pa[1], (double)pa[2]);
+        d3 e1 = mk3((double)pb[0], (double)pb[1], (double)pb[2]) - a;
+        d3 e2 = mk3((double)pc[0], (double)pc[1], (double)pc[2]) - a;
+        double2* t = tris + (size_t)i * kTriD2;
+        t[0] = make_double2(a.x, a.y);
+        t[1] = make_double2(a.z, e1.x);
+        t[2] = make_double2(e1.y, e1.z);
+        t[3] = make_double2(e2.x, e2.y);
+        t[4] = make_double2(e2.z, __longlong_as_double((long long)f));
+    }
+}
+#endif
+
 __global__ void emit_tris_kernel(const int32_t* __restrict__ F, const float* __restrict__ V,
                                  const uint64_t* __restrict__ keys, int n, double2* __restrict__ tris)
 {

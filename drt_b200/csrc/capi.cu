@@ -282,12 +282,18 @@ int fit_and_emit(drt_bvh* b, cudaStream_t st, const double* pending_V64 = nullpt
     if (n > 1) CU(cudaMemsetAsync(b->flags, 0, sizeof(int) * (size_t)(n - 1), st));
     fit_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_keys, n, b->children, b->parent, b->blo, b->bhi,
                                                     b->flags); ++g_launches;
+#if DRT_QNODE
+    emit_all_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, b->F, b->V32, b->sorted_keys, b->children, b->blo, b->bhi, b->scene, b->nodes,
+                                                        DRT_BVH4 ? b->nodes4 : nullptr, b->tris);
+    ++g_launches;
+#else
     grid_kernel<<<1, 32, 0, st>>>(b->blo, b->bhi, b->scene); ++g_launches;
     emit_nodes_kernel<<<blocks_for(n > 1 ? n - 1 : 1, 256), 256, 0, st>>>(n, b->children, b->blo, b->bhi, b->scene, b->nodes); ++g_launches;
 #if DRT_QNODE && DRT_BVH4
     emit_nodes4_kernel<<<blocks_for(n > 1 ? n - 1 : 1, 256), 256, 0, st>>>(n, b->children, b->blo, b->bhi, b->scene, b->nodes4); ++g_launches;
 #endif
     emit_tris_kernel<<<blocks_for(n, 256), 256, 0, st>>>(b->F, b->V32, b->sorted_keys, n, b->tris); ++g_launches;
+#endif
     CU(cudaGetLastError());
     return DRT_OK;
 }

@@ -84,7 +84,8 @@ if os.path.exists(rep):
     summ = {}
     with open(os.path.join(out_dir, f"{tag}_ncu_full.md"), "w") as f:
         f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` of one bench step\n"
-                "(`python bench.py --steps 1 --warmup 3 --views 8 --profile-from-start off`, C4 mesh, 8 views = 5 529 600 rays per launch).\n\n")
+                f"(`python bench.py --steps 1 --warmup 3 [--views V] --graph off` under `--profile-from-start off`; C4 mesh, {RAYS:,} rays per launch;\n"
+                f"kernel sources hash {_build.source_hash()}).\n\n")
         for r in rows[2:]:
             name = short(r[hdr.index("Kernel Name")])
             f.write(f"## `{name}`\n\n| metric | value |\n|---|---:|\n")
