@@ -529,6 +529,7 @@ def run_b200(args):
     probe = None
     use_graph = args.loss_path == "step" and n_local > 0 and (args.graph == "on" or (args.graph == "auto" and n_local <= 8_000_000))
     graph = None
+    graph_launches = 0
     if use_graph:
         # phase split (build / forward / backward) from a few stream-launched steps: a graph has no event boundaries inside
         pm = [[ev() for _ in range(6)] for _ in range(3)]
@@ -551,9 +552,11 @@ def run_b200(args):
                 V.grad = None
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
+            cap0 = lib.drt_kernel_launches()
             with torch.cuda.graph(graph):
                 loss_buf.zero_()
                 step(origin, ray_dir, screen, valid, g_dir)
+            graph_launches = lib.drt_kernel_launches() - cap0   # kernels of this library inside ONE replay
             for _ in range(2):
                 graph.replay()
             sync_all()
@@ -594,6 +597,8 @@ def run_b200(args):
     sampler.active = False
     t_wall = time.perf_counter() - t_wall0
     launches = lib.drt_kernel_launches() - launches0
+    if graph is not None:
+        launches += graph_launches * args.steps   # a replay launches the captured kernels without passing through the library's counter
     sync_all()
     t_total_ms = start.elapsed_time(end)
     phases = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / args.steps for i in range(5)]

@@ -801,7 +801,11 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
     for (int k = 0; k < n_lanes; ++k) {  // Q1: entry query
         Lane& l = lane[k];
         // whole images of image_w x image_h pixels that a 32-pixel tile shape divides: a warp's batch becomes a pixel tile
+#if DRT_FUSE_R
+        LossEntryJob j1{rays, l.L, l.countL, tile_map(image_w, image_h, l.n, false), (int)l.base, RefractCtx{V64, b->F, ext_ior, int_ior}, l.park};
+#else
         LossEntryJob j1{rays, l.L, l.countL, tile_map(image_w, image_h, l.n, false), (int)l.base};
+#endif
         if (l.base % 32 != 0 || (j1.tiles.img_w && l.base % j1.tiles.img_hw != 0)) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: internal lane split is not tile aligned");
 #if DRT_QNODE
         if (beam) {
@@ -822,13 +826,19 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
     }
     for (int k = 0; k < n_lanes; ++k) {  // R1 + Q2: refraction at the entry hit, exit query
         Lane& l = lane[k];
+#if DRT_FUSE_R
+        LossExitJob j2{l.park, l.L, RefractCtx{V64, b->F, ext_ior, int_ior}, tgt, l.M, l.countM};
+#else
         ls_r1_kernel<<<l.dgrid, 128, 0, ls[k]>>>(b->view(), V64, rays, ext_ior, int_ior, l.L, l.countL, l.park);
         LossExitJob j2{l.park, l.L};
+#endif
         DRT_LAUNCH_Q(ls_q2_kernel, l.pg, ls[k], b->view(), j2, l.countL, l.ctl + 1, pol[1]);
     }
     for (int k = 0; k < n_lanes; ++k) {  // R2 + Q3: refraction at the exit hit (+ target lookup), occlusion query
         Lane& l = lane[k];
+#if !DRT_FUSE_R
         ls_r2_kernel<<<l.dgrid, 128, 0, ls[k]>>>(b->view(), V64, ext_ior, int_ior, l.L, l.countL, l.park, tgt, l.M, l.countM);
+#endif
         LossOcclusionJob j3{l.park, l.M, l.L, l.S, l.countS};
         DRT_LAUNCH_Q(ls_q3_kernel, l.pg, ls[k], b->view(), j3, l.countM, l.ctl + 2, pol[2]);
     }

@@ -109,6 +109,47 @@ struct Park {
     }
 };
 
+// DRT_FUSE_R = 1: the refraction passes R1 / R2 run at the RETIRE of the entry / exit query (all lanes of a warp retire together,
+// so the float64 code runs converged) instead of as two dense kernels over the list: two launches and two stage boundaries less
+// per step.  Out of line, so that the traversal loop keeps its registers.
+#ifndef DRT_FUSE_R
+#define DRT_FUSE_R 0
+#endif
+
+struct RefractCtx {
+    const double* __restrict__ V64;
+    const int32_t* __restrict__ F;
+    double ext_ior, int_ior;
+};
+
+// entry hit of ray (o, d) on triangle id: refracted ray -> park slot; false on total internal reflection
+__device__ __noinline__ bool refract_entry(const RefractCtx c, const double* __restrict__ origin3, const double* __restrict__ dir3, int id,
+                                           Park park, int slot)
+{
+    const int32_t* f = c.F + 3 * (size_t)id;
+    HitRec h;
+    d3 o1, d1;
+    hit_forward(h, ld3(origin3), ld3(dir3), ld3(c.V64 + 3 * (size_t)f[0]), ld3(c.V64 + 3 * (size_t)f[1]), ld3(c.V64 + 3 * (size_t)f[2]),
+                c.ext_ior, c.int_ior, o1, d1);
+    if (h.tir) return false;
+    park.store(slot, o1, d1);
+    return true;
+}
+
+// exit hit of the parked ray of `slot` on triangle id: exit ray parked in place; false on total internal reflection
+__device__ __noinline__ bool refract_exit(const RefractCtx c, int id, Park park, int slot)
+{
+    const int32_t* f = c.F + 3 * (size_t)id;
+    HitRec h;
+    d3 o1, d1, o2, d2;
+    park.load(slot, o1, d1);
+    hit_forward(h, o1, d1, ld3(c.V64 + 3 * (size_t)f[0]), ld3(c.V64 + 3 * (size_t)f[1]), ld3(c.V64 + 3 * (size_t)f[2]), c.ext_ior, c.int_ior, o2,
+                d2);
+    if (h.tir) return false;
+    park.store(slot, o2, d2);
+    return true;
+}
+
 // ---- Q1: entry query over all rays; only hits leave a trace ---------------------------------------
 // Work item -> ray through TileMap (trace.cuh): with the image size known a warp's batch is an 8 x 4 pixel tile
 // (the warp scheduling model, tools/warp_sim, gives -22 % warp-wide steps for Q1 and -10 % for Q2/Q3).
@@ -122,6 +163,10 @@ struct LossEntryJob {
     int* __restrict__ countL;
     TileMap tiles;
     int base;  // first ray of this launch's share of the batch (drt_ray_loss_step may split a batch over two streams)
+#if DRT_FUSE_R
+    RefractCtx rc;
+    Park park;
+#endif
     __device__ __forceinline__ int ray_of(int item) const { return tiles.ray_of(item + base); }
     __device__ __forceinline__ bool load(int item, d3& o, d3& d) const
     {
@@ -139,7 +184,16 @@ struct LossEntryJob {
     __device__ __forceinline__ void retire(int item, int id, double) const
     {
         int slot = warp_append<>(countL, id >= 0);
-        if (slot >= 0) L[slot] = make_int4(ray_of(item), id, -1, 0);
+        if (slot >= 0) {
+            const int i = ray_of(item);
+#if DRT_FUSE_R
+            const int64_t row = rays.rpo > 1 ? i / rays.rpo : i;
+            const bool ok = refract_entry(rc, rays.origin + 3 * row, rays.dir + 3 * (int64_t)i, id, park, slot);
+            L[slot] = make_int4(i, id, -1, ok ? 0 : 1);
+#else
+            L[slot] = make_int4(i, id, -1, 0);
+#endif
+        }
     }
 };
 
@@ -190,13 +244,27 @@ struct LossExitJob {
     __device__ __forceinline__ void finish(unsigned) {}
     Park park;
     int4* __restrict__ L;
+#if DRT_FUSE_R
+    RefractCtx rc;
+    TargetSrc tgt;
+    int2* __restrict__ M;
+    int* __restrict__ countM;
+#endif
     __device__ __forceinline__ bool load(int k, d3& o, d3& d) const
     {
         if (L[k].w) return false;
         park.load(k, o, d);
         return true;
     }
-    __device__ __forceinline__ void retire(int k, int id, double) const { L[k].z = id; }
+    __device__ __forceinline__ void retire(int k, int id, double) const
+    {
+        L[k].z = id;
+#if DRT_FUSE_R
+        const bool alive = id >= 0 && !L[k].w && refract_exit(rc, id, park, k);
+        int slot = warp_append<>(countM, alive);
+        if (slot >= 0) M[slot] = make_int2(k, tgt.find(L[k].x));
+#endif
+    }
 };
 
 template <int MINB>
