@@ -24,9 +24,12 @@ def limit_hook(grad, cap=1.0):  # optim.py:155-162
     return grad.clamp(-cap, cap)
 
 
-def optimize(vertices0, faces, data, hp, iters, log_every=10, fused_loss=True):
+def optimize(vertices0, faces, data, hp, iters, log_every=10, fused_loss=True, remesh_len=None):
     Render.intIOR, Render.resy, Render.resx = hp["IOR"], data.resy, data.resx   # optim.py:178-180
     scene = Render.Scene(vertices=vertices0, faces=faces)
+    if remesh_len:  # optim.py:198 `meshlabserver.remesh(scene, remesh_len)`, served by the in-tree stand-in (no MeshLab here)
+        from drt_b200 import remesh
+        remesh.Remesher().remesh(scene, remesh_len)
     init_vertices = scene.vertices
     parameter = torch.zeros_like(init_vertices, requires_grad=True)
     parameter.register_hook(limit_hook)

@@ -140,3 +140,44 @@ def test_optim_py_call_sequence_on_gpu(tmp_path, cuda_device):
     assert np.abs(final - exported[1]).max() > 1e-4
     assert scene.optix_mesh.info()["builds"] >= 2 * 4  # a rebuild per update_verticex, like DiffRender.py:380
     assert os.path.getsize(tmp_path / "recons.ply") > 0
+
+
+@pytest.mark.gpu
+def test_coarse_to_fine_passes_with_the_remesh_stand_in(tmp_path, cuda_device):
+    """optim.py:189-217 with `meshlabserver.remesh(scene, remesh_len)` served by drt_b200.remesh.Remesher: every pass exports the
+    optimised mesh, refines it to a shorter target edge length and reloads it through Scene.update_mesh (rebuilding the BVH and
+    the edge tables); the ray loss keeps working on the refined mesh."""
+    import drt_b200.DiffRender as Render
+    from drt_b200 import configs, losses, meshgen, plyio, remesh, synthetic_data
+    v, f = configs.load_mesh("hand_vh")
+    path = tmp_path / "hand_vh.ply"
+    plyio.write_ply(str(path), v, f)
+    Render.intIOR = 1.4723
+    data = synthetic_data.SyntheticData(configs.perturbed_target_mesh(v, scale=1.5), f, 120, 160, n_views=6, num_view=6, int_ior=Render.intIOR)
+    Render.resy, Render.resx = data.resy, data.resx
+    scene = Render.Scene(str(path))
+    remesher = remesh.Remesher(str(tmp_path))
+    ray_view = data.ray_view_generator()
+    n_faces, losses_seen = [scene.faces.shape[0]], []
+    for remesh_len in (3.0, 2.2):                                       # interp_R(start_len, end_len, ...) of optim.py:192
+        remesher.remesh(scene, remesh_len)                              # optim.py:198
+        assert scene.mesh.is_watertight
+        n_faces.append(scene.faces.shape[0])
+        init_vertices = scene.vertices
+        parameter = torch.zeros_like(init_vertices, requires_grad=True)
+        parameter.register_hook(lambda g: torch.nan_to_num(g, nan=0.0).clamp(-1.0, 1.0))
+        opt = torch.optim.SGD([parameter], lr=0.05, momentum=0.9, nesterov=True)
+        for _ in range(3):
+            opt.zero_grad()
+            scene.update_verticex(init_vertices + parameter)
+            loss = losses.ray_loss_view(scene, data.get_view_compact(next(ray_view)))
+            loss.backward()
+            assert torch.isfinite(loss) and parameter.grad.abs().max() > 0
+            losses_seen.append(loss.item())
+            opt.step()
+        # the export the next pass starts from holds the optimised vertices of THIS pass
+        exported = plyio.read_ply(scene.mesh.export(str(tmp_path / "check.ply")))[0]
+        now = scene.vertices.detach().cpu().numpy()
+        assert exported.shape == now.shape and np.abs(exported - now).max() <= 1e-5 * max(1.0, np.abs(now).max())
+    assert n_faces[0] < n_faces[1] < n_faces[2]
+    assert scene.optix_mesh.info()["n_faces"] == n_faces[2] and scene.dihedral_angle().shape[0] == n_faces[2] * 3 // 2
