@@ -313,45 +313,52 @@ def optim_iteration_bench(dev, mesh_name="mouse_vh", resy=960, resx=1280, n_view
     for k in range(n_views):
         data.get_view(k)
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    marks = []
 
-    def iteration(record):
-        m = [ev() for _ in range(5)] if record else None
+    def iteration(fused, m):
         opt.zero_grad()
         if m: m[0].record()
         scene.update_verticex(init + parameter)
         ray_loss = losses.ray_loss_view(scene, compact[next(ray_view)])
         if m: m[1].record()
         vh_loss = torch.zeros((), dtype=torch.float64, device=dev)
-        for _ in range(8):
-            _, _, sil, origin, _, cam = data.get_view(next(silh_view))
-            edges = scene.silhouette_edge(origin[0])
-            index, output = scene.primary_visibility(edges, cam, origin[0], detach_depth=True)
-            vh_loss = vh_loss + (sil.view(resy, resx)[index[:, 1], index[:, 0]] - output).abs().sum()
+        batch = [data.get_view(next(silh_view)) for _ in range(8)]                # optim.py:72: 8 silhouette views per iteration
+        if fused:          # optim.py:72-79 for all 8 views in ONE launch, no sync (losses.silhouette_loss -> drt_silhouette_loss)
+            vh_loss = losses.silhouette_loss(scene, [(sil, cam, origin[0]) for _, _, sil, origin, _, cam in batch], detach_depth=True)
+        else:              # the reference's own call sequence on the drop-in Scene methods
+            for _, _, sil, origin, _, cam in batch:
+                edges = scene.silhouette_edge(origin[0])
+                index, output = scene.primary_visibility(edges, cam, origin[0], detach_depth=True)
+                vh_loss = vh_loss + (sil.view(resy, resx)[index[:, 1], index[:, 0]] - output).abs().sum()
         if m: m[2].record()
-        sm_loss = (-torch.log(1 + scene.dihedral_angle())).sum()
+        sm_loss = losses.smoothness_loss(scene) if fused else (-torch.log(1 + scene.dihedral_angle())).sum()
         loss = hp["ray_w"] * 217.5 / resy / resy * ray_loss + hp["vh_w"] * 217.5 / resy * vh_loss + hp["sm_w"] * scene.mean_len / 10 * sm_loss
         if m: m[3].record()
         loss.backward()
         opt.step()
-        if m:
-            m[4].record()
-            marks.append(m)
+        if m: m[4].record()
 
-    for _ in range(warmup):
-        iteration(False)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for _ in range(iters):
-        iteration(True)
-    torch.cuda.synchronize(dev)
-    wall = (time.perf_counter() - t0) / iters
-    ph = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / iters for i in range(4)]
-    return {"workload": f"{mesh_name} ({len(f)} tris), one optim.py iteration: 1 ray view {resx}x{resy} + 8 silhouette views + smoothness + backward + SGD step",
-            "ms_per_iteration": sum(ph), "wall_ms_per_iteration": 1e3 * wall, "iterations": iters,
-            "phases_ms": {"rebuild+ray_loss": ph[0], "silhouette_8_views": ph[1], "smoothness+total": ph[2], "backward+sgd": ph[3]},
-            "primary_rays_per_iteration": resy * resx, "rays_per_s": resy * resx / (sum(ph) * 1e-3),
-            "note": "device time between CUDA events; the silhouette path syncs once per view (data-dependent output sizes, as in the reference)"}
+    out = {"workload": f"{mesh_name} ({len(f)} tris), one optim.py iteration: 1 ray view {resx}x{resy} + 8 silhouette views + smoothness + backward + SGD step",
+           "primary_rays_per_iteration": resy * resx,
+           "note": "device time between CUDA events. drop_in: ray loss fused (losses.ray_loss_view), silhouette and smoothness terms through the "
+                   "reference's own Scene methods (two host syncs per silhouette view: data-dependent output sizes, as in the reference); fused: "
+                   "all three terms through the fused calls (losses.silhouette_loss / smoothness_loss), no sync inside the iteration"}
+    for name, fused in (("drop_in", False), ("fused", True)):
+        marks = []
+        for _ in range(warmup):
+            iteration(fused, None)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            m = [ev() for _ in range(5)]
+            iteration(fused, m)
+            marks.append(m)
+        torch.cuda.synchronize(dev)
+        wall = (time.perf_counter() - t0) / iters
+        ph = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / iters for i in range(4)]
+        out[name] = {"ms_per_iteration": sum(ph), "wall_ms_per_iteration": 1e3 * wall, "iterations": iters,
+                     "phases_ms": {"rebuild+ray_loss": ph[0], "silhouette_8_views": ph[1], "smoothness+total": ph[2], "backward+sgd": ph[3]},
+                     "rays_per_s": resy * resx / (sum(ph) * 1e-3)}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -819,11 +826,14 @@ def run_b200(args):
             assert abs(loss_host.item() - loss_val) <= tol * max(1.0, abs(loss_val)), (loss_host.item(), loss_val)
             return te.item() / k_e2e, k_e2e
 
-        # pinned host -> device copy bandwidth of this GPU, measured now (256 MiB, best of 4): the ceiling of any e2e number
-        probe = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
-        probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        # pinned host -> device copy bandwidth of this GPU, measured now (512 MiB, best of 6 after a warm-up): the ceiling of any e2e number
+        probe = torch.empty(512 << 20, dtype=torch.uint8).pin_memory()
+        probe.zero_()                                         # touch every page before timing
+        probe_d = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+        probe_d.copy_(probe, non_blocking=True)               # warm-up copy
+        torch.cuda.synchronize(dev)
         h2d_peak = 0.0
-        for _ in range(4):
+        for _ in range(6):
             pa, pb = ev(), ev()
             pa.record()
             probe_d.copy_(probe, non_blocking=True)

@@ -34,6 +34,8 @@ SIGNATURES = {
     "drt_silhouette_classify": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "drt_silhouette_sample": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "drt_silhouette_backward": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "drt_silhouette_loss": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, C.c_int, _vp, _vp, _vp, _vp]),
+    "drt_dihedral_loss": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "drt_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _i64, C.POINTER(_vp)]),
     "drt_comm_handle": (C.c_int, [_vp, C.c_char_p]),
     "drt_comm_connect": (C.c_int, [_vp, C.c_char_p]),

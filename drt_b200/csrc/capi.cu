@@ -739,7 +739,9 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
     int n_lanes = 1;
     int64_t cut[kMaxLanes + 1] = {0, N, N, N, N};  // lane k = rays [cut[k], cut[k+1])
     if (tuning().lanes >= 2 && b->lane_stream[0] && N >= (1 << 17) && (N <= tuning().lanes_max_rays || tuning().lanes_forced)) {
-        const int64_t unit = (img > 0 && N % img == 0) ? img : (img == 0 ? 32 : 0);  // split at image boundaries (else at 32-ray batches)
+        // split at image boundaries when there are enough images, else at 32-ray batches (= pixel tiles: the item -> ray map
+        // below is the one of the WHOLE batch, so a lane may start in the middle of an image)
+        const int64_t unit = (img > 0 && N % img == 0 && N / img >= tuning().lanes) ? img : 32;
         if (unit > 0) {
             const int64_t units = N / unit;
             n_lanes = (int)std::min<int64_t>(tuning().lanes, std::max<int64_t>(1, units));
@@ -802,11 +804,11 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
         Lane& l = lane[k];
         // whole images of image_w x image_h pixels that a 32-pixel tile shape divides: a warp's batch becomes a pixel tile
 #if DRT_FUSE_R
-        LossEntryJob j1{rays, l.L, l.countL, tile_map(image_w, image_h, l.n, false), (int)l.base, RefractCtx{V64, b->F, ext_ior, int_ior}, l.park};
+        LossEntryJob j1{rays, l.L, l.countL, tile_map(image_w, image_h, N, false), (int)l.base, RefractCtx{V64, b->F, ext_ior, int_ior}, l.park};
 #else
-        LossEntryJob j1{rays, l.L, l.countL, tile_map(image_w, image_h, l.n, false), (int)l.base};
+        LossEntryJob j1{rays, l.L, l.countL, tile_map(image_w, image_h, N, false), (int)l.base};
 #endif
-        if (l.base % 32 != 0 || (j1.tiles.img_w && l.base % j1.tiles.img_hw != 0)) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: internal lane split is not tile aligned");
+        if (l.base % 32 != 0) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: internal lane split is not tile aligned");
 #if DRT_QNODE
         if (beam) {
             // beam pass over all tiles -> list of the surviving tiles (in the lane's part of listS, free until Q3) -> per-ray
@@ -943,6 +945,55 @@ int drt_silhouette_backward(const double* V64, const int64_t* edges, const doubl
     const int grid = (int)std::min<int64_t>(blocks_for(m, 128), (int64_t)sms * 8);
     silhouette_backward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(V64, edges, Camera{R, K, nullptr, nullptr}, detach_depth, f, kept_idx,
                                                                        g_output, m, grad_V);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_silhouette_loss(const drt_bvh* b, const double* V64, const int64_t* edges, const int32_t* e2f, int64_t nE, int32_t n_views,
+                        const double* const* R, const double* const* K, const double* const* R_inverse, const double* const* K_inverse,
+                        const double* const* origin3, const double* const* mask, int32_t resx, int32_t resy, int detach_depth,
+                        double* loss_sum, double* grad_V, int32_t* n_samples, void* stream)
+{
+    if (!b) return fail(DRT_ERR_INVALID, "drt_silhouette_loss: null handle");
+    if (!b->built) return fail(DRT_ERR_STATE, "drt_silhouette_loss: no mesh has been set (update_mesh first)");
+    if (nE < 0 || resx <= 0 || resy <= 0 || n_views < 0) return fail(DRT_ERR_INVALID, "drt_silhouette_loss: bad size");
+    if (nE == 0 || n_views == 0) return DRT_OK;
+    if (!V64 || !edges || !e2f || !R || !K || !R_inverse || !K_inverse || !origin3 || !mask || !loss_sum)
+        return fail(DRT_ERR_INVALID, "drt_silhouette_loss: null buffer");
+    DeviceGuard g(b->device);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", b->device);
+    const int gx = (int)std::min<int64_t>(blocks_for(nE, 128), (int64_t)b->sm_count * 8);
+    for (int v0 = 0; v0 < n_views; v0 += kMaxSilhouetteViews) {  // up to 8 views per launch
+        const int nv = std::min<int>(kMaxSilhouetteViews, n_views - v0);
+        SilhouetteViews sv{};
+        for (int k = 0; k < nv; ++k) {
+            if (!R[v0 + k] || !K[v0 + k] || !R_inverse[v0 + k] || !K_inverse[v0 + k] || !origin3[v0 + k] || !mask[v0 + k])
+                return fail(DRT_ERR_INVALID, "drt_silhouette_loss: null per-view pointer (view %d)", v0 + k);
+            sv.cam[k] = Camera{R[v0 + k], K[v0 + k], R_inverse[v0 + k], K_inverse[v0 + k]};
+            sv.origin[k] = origin3[v0 + k];
+            sv.mask[k] = mask[v0 + k];
+        }
+        silhouette_loss_kernel<<<dim3(gx, nv), 128, 0, (cudaStream_t)stream>>>(b->view(), V64, edges, e2f, nE, sv, resx, resy, detach_depth, loss_sum,
+                                                                               grad_V, n_samples);
+        ++g_launches;
+    }
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_dihedral_loss(const double* V64, const int32_t* e2f, int64_t nE, double* loss_sum, double* grad_V, void* stream)
+{
+    if (nE < 0) return fail(DRT_ERR_INVALID, "drt_dihedral_loss: nE < 0");
+    if (nE == 0) return DRT_OK;
+    if (!V64 || !e2f || !loss_sum) return fail(DRT_ERR_INVALID, "drt_dihedral_loss: null buffer");
+    int dev = 0, sms = 148;
+    CU(device_of(loss_sum, &dev));
+    DeviceGuard g(dev);
+    if (!g.ok) return fail(DRT_ERR_CUDA, "cudaSetDevice(%d) failed", dev);
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<int64_t>(blocks_for(nE, 256), (int64_t)sms * 8);
+    dihedral_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(V64, e2f, nE, loss_sum, grad_V);
     ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;

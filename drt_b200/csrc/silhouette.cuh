@@ -144,4 +144,147 @@ __global__ void __launch_bounds__(128) silhouette_backward_kernel(const double* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// The two loss terms around the ray loss in one optim.py iteration, FUSED like drt_ray_loss_step fuses the ray loss: value and
+// vertex gradient from one launch, no intermediate tensors, no host synchronisation (the drop-in methods above have to return
+// data-dependent-size tensors and therefore sync twice per view; a whole iteration measured 5.9 ms with them, of which the
+// ray path is 0.6 ms).
+//
+//   silhouette_loss_kernel : Loss_calculator.vh_loss (optim.py:67-80), up to 8 views per launch (blockIdx.y = view): silhouette_edge + primary_visibility +
+//       primary_edge_sample + `(mask[index] - output).abs().sum()` + its backward.  One thread per edge of the mesh: classify;
+//       a silhouette edge projects its ends, traces the two probe rays, and if the sample is kept adds |mask[y,x] - 0.5| to the
+//       loss and  d loss/d output = -sign(mask[y,x] - 0.5)  times the reference's dE_pos = -N f, chained through the
+//       projection, to grad_V.
+//   dihedral_loss_kernel   : Loss_calculator.sm_loss (optim.py:82-89): sum over edges of -log(1 + n1.n2) with the analytic
+//       gradient through both unit face normals (DiffRender.py:150-163, 440-443).
+// ------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void add3(double* __restrict__ g, d3 v)
+{
+    atomicAdd(g, v.x);
+    atomicAdd(g + 1, v.y);
+    atomicAdd(g + 2, v.z);
+}
+
+constexpr int kMaxSilhouetteViews = 8;  // optim.py:72 uses 8 views per iteration
+struct SilhouetteViews {  // per-view device pointers, passed by value; blockIdx.y selects the view
+    Camera cam[kMaxSilhouetteViews];
+    const double* origin[kMaxSilhouetteViews];
+    const double* mask[kMaxSilhouetteViews];
+};
+
+__global__ void __launch_bounds__(128) silhouette_loss_kernel(BvhView B, const double* __restrict__ V, const int64_t* __restrict__ edges,
+                                                              const int32_t* __restrict__ e2f, int64_t nE, SilhouetteViews views,
+                                                              int resx, int resy, int detach_depth, double* __restrict__ loss_sum,
+                                                              double* __restrict__ gV, int* __restrict__ n_samples)
+{
+    const Camera cam = views.cam[blockIdx.y];
+    const double* __restrict__ mask = views.mask[blockIdx.y];
+    const d3 o = ld3(views.origin[blockIdx.y]);
+    double acc = 0.0;
+    int kept = 0;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nE; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t* f1 = e2f + 6 * e;
+        const int32_t* f2 = f1 + 3;
+        const double d1 = dot(unit_face_normal(V, f1), o - ld3(V + 3 * (size_t)f1[0]));
+        const double d2 = dot(unit_face_normal(V, f2), o - ld3(V + 3 * (size_t)f2[0]));
+        if ((d1 > 0.0) == (d2 > 0.0)) continue;                                   // not a silhouette edge (DiffRender.py:456)
+        const int64_t va = edges[2 * e], vb = edges[2 * e + 1];
+        d3 pa, pb;
+        project(cam, ld3(V + 3 * (size_t)va), pa);
+        project(cam, ld3(V + 3 * (size_t)vb), pb);
+        const double ax = __ddiv_rn(pa.x, pa.z), ay = __ddiv_rn(pa.y, pa.z), bx = __ddiv_rn(pb.x, pb.z), by = __ddiv_rn(pb.y, pb.z);
+        const double mx = __ddiv_rn(addr(ax, bx), 2.0), my = __ddiv_rn(addr(ay, by), 2.0);
+        const double nx = subr(ay, by), ny = subr(bx, ax);
+        const double len = __dsqrt_rn(addr(mulr(nx, nx), mulr(ny, ny)));
+        const double ux = __ddiv_rn(nx, len), uy = __ddiv_rn(ny, len);
+        int cover[2];
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const double px = side ? subr(mx, ux) : addr(mx, ux), py = side ? subr(my, uy) : addr(my, uy);
+            double tt;
+            int id;
+            traverse<true>(B, cast_ray(o, probe_direction(cam, px, py, o)), tt, id);
+            cover[side] = id >= 0 ? 1 : 0;
+        }
+        const double f = (double)(cover[0] - cover[1]);
+        const int64_t ix = (int64_t)mx, iy = (int64_t)my;
+        if (!(fabs(f) > 1e-5 && ix < resx - 1 && iy < resy - 1 && ix >= 0 && iy >= 0)) continue;
+        const double diff = mask[iy * (int64_t)resx + ix] - 0.5;                  // output = 0.5 (DiffRender.py:240), optim.py:79
+        acc += fabs(diff);
+        ++kept;
+        if (gV) {
+            const double g_out = diff > 0.0 ? -1.0 : (diff < 0.0 ? 1.0 : 0.0);    // d |mask - output| / d output
+            const double s = -f * g_out;
+            const double gx = nx * s, gy = ny * s;                                // w.r.t. the pixel position of either end
+#pragma unroll
+            for (int end = 0; end < 2; ++end) {
+                const d3 p = end ? pb : pa;
+                const d3 gp = mk3(gx / p.z, gy / p.z, -(gx * p.x + gy * p.y) / (p.z * p.z));
+                d3 gc = mk3(__ldg(cam.K + 0) * gp.x + __ldg(cam.K + 3) * gp.y + __ldg(cam.K + 6) * gp.z,
+                            __ldg(cam.K + 1) * gp.x + __ldg(cam.K + 4) * gp.y + __ldg(cam.K + 7) * gp.z,
+                            __ldg(cam.K + 2) * gp.x + __ldg(cam.K + 5) * gp.y + __ldg(cam.K + 8) * gp.z);
+                if (detach_depth) gc.z = 0.0;
+                add3(gV + 3 * (size_t)(end ? vb : va),
+                     mk3(__ldg(cam.R + 0) * gc.x + __ldg(cam.R + 4) * gc.y + __ldg(cam.R + 8) * gc.z,
+                         __ldg(cam.R + 1) * gc.x + __ldg(cam.R + 5) * gc.y + __ldg(cam.R + 9) * gc.z,
+                         __ldg(cam.R + 2) * gc.x + __ldg(cam.R + 6) * gc.y + __ldg(cam.R + 10) * gc.z));
+            }
+        }
+    }
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+        kept += __shfl_xor_sync(0xffffffffu, kept, sft);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (acc != 0.0) atomicAdd(loss_sum, acc);
+        if (n_samples && kept) atomicAdd(n_samples, kept);
+    }
+}
+
+// unit normal of triangle (a, b, c) with what its reverse pass needs
+struct FaceN {
+    d3 e1, e2, n;
+    double L;
+};
+__device__ __forceinline__ FaceN face_normal(const double* __restrict__ V, const int32_t* __restrict__ tri)
+{
+    FaceN r;
+    const d3 a = ld3(V + 3 * (size_t)tri[0]);
+    r.e1 = ld3(V + 3 * (size_t)tri[1]) - a;
+    r.e2 = ld3(V + 3 * (size_t)tri[2]) - a;
+    const d3 N = cross(r.e1, r.e2);
+    r.L = __dsqrt_rn(dot(N, N));
+    r.n = divs(N, r.L);
+    return r;
+}
+// gradient g_n w.r.t. the unit normal -> the three vertices (same chain as common.cuh:hit_backward's normal part)
+__device__ __forceinline__ void face_normal_backward(const FaceN& fc, d3 g_n, const int32_t* __restrict__ tri, double* __restrict__ gV)
+{
+    const d3 g_N = (g_n - fc.n * dot(fc.n, g_n)) * __ddiv_rn(1.0, fc.L);
+    const d3 g_e1 = cross(fc.e2, g_N), g_e2 = cross(g_N, fc.e1);
+    add3(gV + 3 * (size_t)tri[1], g_e1);
+    add3(gV + 3 * (size_t)tri[2], g_e2);
+    add3(gV + 3 * (size_t)tri[0], -(g_e1 + g_e2));
+}
+
+__global__ void __launch_bounds__(256) dihedral_loss_kernel(const double* __restrict__ V, const int32_t* __restrict__ e2f, int64_t nE,
+                                                            double* __restrict__ loss_sum, double* __restrict__ gV)
+{
+    double acc = 0.0;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nE; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t* f1 = e2f + 6 * e;
+        const int32_t* f2 = f1 + 3;
+        const FaceN a = face_normal(V, f1), b = face_normal(V, f2);
+        const double c = dot(a.n, b.n);                                            // DiffRender.py:440-443
+        acc += -log(1.0 + c);                                                      // optim.py:86-87
+        if (gV) {
+            const double g_c = -1.0 / (1.0 + c);
+            face_normal_backward(a, b.n * g_c, f1, gV);
+            face_normal_backward(b, a.n * g_c, f2, gV);
+        }
+    }
+    for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+    if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(loss_sum, acc);
+}
+
 }  // namespace drt

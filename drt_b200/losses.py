@@ -186,3 +186,82 @@ def ray_loss(scene, origin, ray_dir, screen=None, valid=None, targets=None, n_pa
 def ray_loss_view(scene, view):
     """`view` = captured_data.CompactView (one origin row, ray_dir, sparse targets) on the scene's device."""
     return ray_loss(scene, view.origin, view.ray_dir, targets=view.targets, image_size=getattr(view, "image_size", None))
+
+
+class SilhouetteLoss(torch.autograd.Function):
+    """Loss_calculator.vh_loss (optim.py:67-80) for a list of views from ONE call of drt_silhouette_loss (up to 8 views per launch):
+    value and vertex gradient, no intermediate tensors, no host synchronisation."""
+
+    @staticmethod
+    def forward(ctx, vertices, mesh, Edges, E2F32, views, resy, resx, detach_depth, n_samples):
+        dev = mesh.device
+        V = vertices.detach().contiguous()
+        optix.check_on(dev, vertices=V, Edges=Edges, E2F=E2F32, n_samples=n_samples)
+        if V.dtype != torch.float64 or Edges.dtype != torch.long or E2F32.dtype != torch.int32:
+            raise TypeError("silhouette_loss needs float64 vertices, Edges long [E,2] and the int32 E2F table")
+        keep, cols = [], [[] for _ in range(6)]
+        for mask, camera_M, origin in views:
+            R, K, R_inv, K_inv = (m.detach().to(torch.float64).contiguous() for m in camera_M)
+            o = origin.detach().to(torch.float64).contiguous()
+            mk = mask.detach().to(torch.float64).contiguous()
+            optix.check_on(dev, R=R, K=K, R_inverse=R_inv, K_inverse=K_inv, origin=o, mask=mk)
+            if mk.numel() != int(resy) * int(resx) or o.shape != (3,) or R.shape != (4, 4) or K.shape != (3, 3) or R_inv.shape != (4, 4) or K_inv.shape != (3, 3):
+                raise ValueError("mask must hold resy*resx values, origin [3], camera_M = (R [4,4], K [3,3], R_inverse [4,4], K_inverse [3,3])")
+            for c, t in zip(cols, (R, K, R_inv, K_inv, o, mk)):
+                c.append(t.data_ptr())
+            keep += [R, K, R_inv, K_inv, o, mk]
+        n = len(views)
+        arrays = [(C.c_void_p * max(n, 1))(*c) for c in cols]
+        loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        grad_V = torch.zeros_like(V) if ctx.needs_input_grad[0] else None
+        _lib.call("drt_silhouette_loss", mesh._h, _ptr(V), _ptr(Edges), _ptr(E2F32), Edges.shape[0], n, *arrays, int(resx), int(resy),
+                  int(bool(detach_depth)), _ptr(loss), _ptr(grad_V), _ptr(n_samples), optix._stream_ptr(dev))
+        st = torch.cuda.current_stream(dev)
+        for t in [V] + keep:
+            t.record_stream(st)
+        ctx.save_for_backward(grad_V)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (grad_V,) = ctx.saved_tensors
+        return (grad_V * g_loss if grad_V is not None else None,) + (None,) * 8
+
+
+def silhouette_loss(scene, mask, camera_M=None, origin=None, detach_depth=True, n_samples=None):
+    """`(mask.view(resy, resx)[index[:,1], index[:,0]] - output).abs().sum()` over the silhouette-edge samples (optim.py:74-79:
+    silhouette_edge -> primary_visibility -> the L1 term), fused.  One view: `mask` = its silhouette image [resy*resx], `camera_M`,
+    `origin` [3] = the camera centre.  Several views (optim.py:72 sums 8 per iteration): `mask` = a list of (mask, camera_M, origin)
+    triples -- they run in one launch.  `n_samples`: optional int32[1] device tensor, incremented by the number of samples used."""
+    views = mask if camera_M is None else [(mask, camera_M, origin)]
+    Edges, _ = scene._edges()
+    return SilhouetteLoss.apply(scene.vertices, scene.optix_mesh, Edges, scene._E2F32, list(views), _R.resy, _R.resx, detach_depth, n_samples)
+
+
+class DihedralLoss(torch.autograd.Function):
+    """Loss_calculator.sm_loss (optim.py:82-89) from one launch of drt_dihedral_loss."""
+
+    @staticmethod
+    def forward(ctx, vertices, E2F32):
+        V = vertices.detach().contiguous()
+        optix.check_on(V.device, E2F=E2F32)
+        if V.dtype != torch.float64 or not V.is_cuda or E2F32.dtype != torch.int32:
+            raise TypeError("smoothness_loss needs float64 CUDA vertices and the int32 E2F table")
+        loss = torch.zeros(1, dtype=torch.float64, device=V.device)
+        grad_V = torch.zeros_like(V) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(V.device):
+            _lib.call("drt_dihedral_loss", _ptr(V), _ptr(E2F32), E2F32.shape[0], _ptr(loss), _ptr(grad_V), optix._stream_ptr(V.device))
+        V.record_stream(torch.cuda.current_stream(V.device))
+        ctx.save_for_backward(grad_V)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (grad_V,) = ctx.saved_tensors
+        return (grad_V * g_loss if grad_V is not None else None), None
+
+
+def smoothness_loss(scene):
+    """sum over edges of -log(1 + cos(dihedral angle))  (optim.py:85-87), fused with its gradient."""
+    scene._edges()
+    return DihedralLoss.apply(scene.vertices, scene._E2F32)

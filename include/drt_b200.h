@@ -231,6 +231,25 @@ DRT_API int drt_silhouette_backward(const double* V64, const int64_t* edges, con
                             void* stream);
 
 /*
+ * The two loss terms around the ray loss, fused like drt_ray_loss_step (value + vertex gradient from one launch, no host sync):
+ *
+ * drt_silhouette_loss replaces Loss_calculator.vh_loss -- optim.py:67-80 (per view: silhouette_edge + primary_visibility +
+ *   primary_edge_sample + `(mask[index[:,1], index[:,0]] - output).abs().sum()`, summed over the views of the iteration, 8 in
+ *   optim.py:72) and its backward: edges int64[nE,2] / e2f int32[nE,2,3] = Scene.Edges / Scene.E2F; R, K, R_inverse, K_inverse,
+ *   origin3, mask = HOST arrays of n_views DEVICE pointers (camera_M of every view, its camera centre, its silhouette image
+ *   float64[resy*resx]); adds the loss to *loss_sum, d loss / d vertices to grad_V (nullable) and the number of kept samples
+ *   to *n_samples (nullable).  Up to 8 views run in one launch.
+ * drt_dihedral_loss replaces Loss_calculator.sm_loss -- optim.py:82-89 (`-log(1 + dihedral_angle).sum()`, DiffRender.py:440-443)
+ *   and its backward through both unit face normals of every edge.
+ */
+DRT_API int drt_silhouette_loss(const drt_bvh* bvh, const double* V64, const int64_t* edges, const int32_t* e2f, int64_t nE,
+                        int32_t n_views, const double* const* R, const double* const* K, const double* const* R_inverse,
+                        const double* const* K_inverse, const double* const* origin3, const double* const* mask,
+                        int32_t resx, int32_t resy, int detach_depth, double* loss_sum, double* grad_V, int32_t* n_samples,
+                        void* stream);
+DRT_API int drt_dihedral_loss(const double* V64, const int32_t* e2f, int64_t nE, double* loss_sum, double* grad_V, void* stream);
+
+/*
  * The one collective of the path -- SURVEY.md 8(e): views are sharded over the GPUs of one box, the mesh and
  * BVH are replicated, grad_V float64[nV,3] is summed once per step (the reference itself is single-GPU,
  * optix_extend.cpp:10, so there is no reference interface to mirror).  One-shot all-reduce over NVLink /

@@ -114,3 +114,48 @@ def test_fused_silhouette_kernels_vs_torch_restatement(cuda_device, mesh, res, v
             assert torch.equal(index, index2) and torch.equal(output, output2) and index.shape[0] > 50
             ga, gb = V.grad.cpu().numpy(), V2.grad.cpu().numpy()
             assert np.abs(ga - gb).max() <= 1e-9 * np.abs(gb).max(), (vid, detach)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("detach", [True, False])
+def test_fused_silhouette_and_smoothness_losses_vs_the_drop_in_path(cuda_device, detach):
+    """losses.silhouette_loss / smoothness_loss (one launch each, no sync) against the same terms written as optim.py writes
+    them (optim.py:74-79, 85-87) on the drop-in Scene methods: value <= 1e-12, vertex gradient <= 1e-9."""
+    import drt_b200.DiffRender as R
+    from drt_b200 import losses, synthetic_data
+    v, f = load_mesh("mouse_vh")
+    resy, resx = 240, 320
+    R.resy, R.resx, R.intIOR = resy, resx, 1.4723
+    data = synthetic_data.SyntheticData(v + 0.8 * np.sin(v[:, [1, 2, 0]] * 0.15), f, resy, resx, n_views=6, num_view=6, int_ior=1.4723)
+    sc = R.Scene(vertices=v, faces=f, cuda_device=cuda_device.index or 0)
+    for vid in (0, 2, 5):
+        _, _, sil, origin, _, cam = data.get_view(vid)
+        Va = sc.vertices.detach().clone().requires_grad_(True)
+        sc.update_verticex(Va)
+        edges = sc.silhouette_edge(origin[0])
+        index, output = sc.primary_visibility(edges, cam, origin[0], detach_depth=detach)
+        ref = (sil.view(resy, resx)[index[:, 1], index[:, 0]] - output).abs().sum() + 0.3 * (-torch.log(1 + sc.dihedral_angle())).sum()
+        ref.backward()
+        Vb = sc.vertices.detach().clone().requires_grad_(True)
+        sc.update_verticex(Vb)
+        n = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+        got = losses.silhouette_loss(sc, sil, cam, origin[0], detach_depth=detach, n_samples=n) + 0.3 * losses.smoothness_loss(sc)
+        got.backward()
+        assert int(n.item()) == index.shape[0] and index.shape[0] > 50
+        assert abs(got.item() - ref.item()) <= 1e-12 * abs(ref.item())
+        ga, gb = Va.grad.cpu().numpy(), Vb.grad.cpu().numpy()
+        assert np.abs(ga - gb).max() <= 1e-9 * np.abs(ga).max()
+    # several views in ONE call (optim.py:72 sums 8 per iteration) = the sum of the single-view calls; 10 views = two launches
+    vids = [0, 1, 2, 3, 4, 5, 0, 2, 4, 1]
+    batch = [data.get_view(k) for k in vids]
+    Vc = sc.vertices.detach().clone().requires_grad_(True)
+    sc.update_verticex(Vc)
+    one = sum(losses.silhouette_loss(sc, sil, cam, origin[0], detach_depth=detach) for _, _, sil, origin, _, cam in batch)
+    one.backward()
+    Vd = sc.vertices.detach().clone().requires_grad_(True)
+    sc.update_verticex(Vd)
+    n = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    many = losses.silhouette_loss(sc, [(sil, cam, origin[0]) for _, _, sil, origin, _, cam in batch], detach_depth=detach, n_samples=n)
+    many.backward()
+    assert abs(many.item() - one.item()) <= 1e-12 * abs(one.item()) and int(n.item()) > 500
+    assert np.abs(Vc.grad.cpu().numpy() - Vd.grad.cpu().numpy()).max() <= 1e-9 * Vc.grad.abs().max().item()
