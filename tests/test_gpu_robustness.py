@@ -126,3 +126,9 @@ def test_cooperative_build_and_no_beam_give_the_same_answers(cuda_device):
                         "-k", "closest_hit or refit or loss_step_vs_oracle or edge_cases"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    # the fused step in 3 forced lanes (internal streams, a lane boundary inside an image) on a whole benchmark view
+    env = dict(os.environ, DRT_LANES="3")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        os.path.join(root, "tests", "test_gpu_headline_parity.py"), "-k", "full_c4_view"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
