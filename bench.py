@@ -62,6 +62,9 @@ def parse():
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step (BVH rebuild + fused ray-loss step + backward) as ONE CUDA graph; auto: when a rank has <= 8 M rays "
                          "per step (launch-bound regime: one view per iteration, or 8 GPUs)")
+    ap.add_argument("--tile-beams", default="prepared", choices=["prepared", "inline"],
+                    help="resident step: per-tile direction intervals of the (fixed) view set prepared once at load time by drt_tile_beams "
+                         "(default, as a DRT run would: the view sets never change), or re-derived from the rays inside every step")
     ap.add_argument("--no-iteration", action="store_true", help="skip the supplementary whole-optim.py-iteration timing")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle check of one view of the timed workload")
     ap.add_argument("--rebalance", type=int, default=3, help="rounds of measured-cost refinement of the balanced view assignment (N > 1)")
@@ -437,6 +440,14 @@ def run_b200(args):
         return origin, ray_dir, screen, valid, origins, losses.SparseTargets.from_dense(screen, valid)
 
     origin, ray_dir, screen, valid, origins, sparse = make_inputs(cams)
+
+    def make_beams():
+        # load-time preparation of the fixed view set (like the compact layout above): per-tile direction intervals, 1.5 B/ray
+        if args.tile_beams == "prepared" and args.loss_path == "step" and n_local:
+            return losses.prepare_tile_beams(origins, ray_dir, (resy, resx))
+        return None
+
+    beams = make_beams()
     g_dir = torch.empty_like(origin) if args.loss_path == "dense" else None
     loss_buf = torch.zeros(1, dtype=torch.float64, device=dev)
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
@@ -455,7 +466,7 @@ def run_b200(args):
             # public fused consumer (optim.py:91-108 + :210 as one autograd.Function = one library call): forward
             # wavefront, then loss + analytic backward over the valid paths; the library records marks[2] between them
             loss = losses.ray_loss(scene, origins, d, targets=sparse, ev_after_fwd=marks[2].cuda_event if marks is not None else None,
-                                   image_size=(resy, resx))
+                                   image_size=(resy, resx), tile_beams=beams)
             if marks is not None: marks[3].record()
             loss.backward()
             loss_buf.add_(loss.detach())
@@ -526,6 +537,7 @@ def run_b200(args):
             del origin, ray_dir, screen, valid, origins, sparse
             torch.cuda.empty_cache()
             origin, ray_dir, screen, valid, origins, sparse = make_inputs(cams)
+            beams = make_beams()
             for _ in range(2):
                 loss_buf.zero_()
                 step(origin, ray_dir, screen, valid, g_dir)
@@ -1019,6 +1031,8 @@ def run_b200(args):
                        "bvh": "refit each step" if args.refit else "full LBVH rebuild each step", "loss_path": args.loss_path,
                        "launch": "one CUDA graph replay per step" if graph is not None else "stream launches",
                        "l2": "inputs larger than L2 (%.1f GB of rays per step per GPU)" % (n_local * 48 / 1e9),
+                       "tile_beams": ("per-tile direction intervals of the fixed view set prepared once at load time (drt_tile_beams, 1.5 B/ray resident)"
+                                      if beams is not None else "derived from the rays inside every step"),
                        "int_ior": configs.INT_IOR, "valid_frac_rank0": valid_frac},
             "phases_ms": {"bvh_build": t_build_ms, "fwd": t_fwd_ms, "loss_grad": phases[2], "bwd": t_bwd_ms, "allreduce": t_ar_ms,
                           "source": "3 stream-launched probe steps (the timed steps replay one CUDA graph)" if graph is not None else "the timed steps"},

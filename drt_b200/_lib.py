@@ -30,6 +30,10 @@ SIGNATURES = {
     "drt_ray_loss_grad_rec": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "drt_ray_loss_step": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _f64, _f64, C.c_int, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
                                     _vp, _vp, _vp, _vp, _vp]),
+    "drt_ray_loss_step_beams": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _f64, _f64, C.c_int, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
+                                          _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drt_tile_beams_floats": (_i64, [_i64]),
+    "drt_tile_beams": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp]),
     "drt_generate_rays": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "drt_silhouette_classify": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "drt_silhouette_sample": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),

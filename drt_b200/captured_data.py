@@ -4,9 +4,9 @@ Schema of the captured sets (captured_data.py:94-108, 136-149): per object one f
 `cam_proj [72,4,4]` (world->camera), `cam_k [3,3]`, `screen_position [72,N,3]` (measured 3-D screen point per
 pixel, zero where nothing was measured), `mask [72,resy,resx]` (uint8 silhouette), and for the Point Grey sets
 calibrated per-pixel `ray_origin/ray_dir [72,N,3]` (the Redmi sets derive rays from K and R, :149).
-The .h5 files themselves are not distributed (README.md:18) and h5py is not in this image, so the loader reads
-the same arrays from an .npz (or from an open h5py.File / any mapping when h5py is available) and keeps the
-72 views in pinned host memory exactly like the reference (:112-120).
+The .h5 files themselves are not distributed (README.md:18) and h5py is not in this image: the loader reads them with
+the in-tree HDF5 reader (`h5lite`; h5py is used when present), or the same arrays from an .npz / any mapping, and keeps
+the 72 views in pinned host memory exactly like the reference (:112-120).
 """
 import numpy as np
 import torch
@@ -32,13 +32,16 @@ def process_mask(M):
 
 
 def open_view_file(path):
-    """-> mapping with the schema above.  .npz always works; .h5 needs h5py."""
+    """-> mapping with the schema above: `f[name][i]`, `f[name][:]` as the reference uses its h5py.File (captured_data.py:94-108).
+    .npz: numpy; .h5 / .hdf5: h5py when it is installed, else the in-tree reader `drt_b200.h5lite` (old- and new-style groups,
+    contiguous / chunked + gzip + shuffle numeric datasets -- what h5py writes by default)."""
     if str(path).endswith((".h5", ".hdf5")):
         try:
             import h5py
-        except ImportError as e:  # pragma: no cover - h5py is absent in this image
-            raise ImportError("reading the captured .h5 sets needs h5py; convert them to .npz with the same keys") from e
-        return h5py.File(path, "r")
+            return h5py.File(path, "r")
+        except ImportError:
+            from . import h5lite
+            return h5lite.File(path)
     return np.load(path)
 
 
@@ -49,11 +52,20 @@ class CompactView:
     pixels (captured_data.py:104: valid = screen_pixel[:,0] != 0).  73 B per ray of the reference layout become
     24 B + 28 B per MEASURED pixel; nothing is rounded."""
 
-    __slots__ = ("origin", "ray_dir", "targets", "mask", "camera_M", "image_size")
+    __slots__ = ("origin", "ray_dir", "targets", "mask", "camera_M", "image_size", "tile_beams")
 
-    def __init__(self, origin, ray_dir, targets, mask=None, camera_M=None, image_size=None):
+    def __init__(self, origin, ray_dir, targets, mask=None, camera_M=None, image_size=None, tile_beams=None):
         self.origin, self.ray_dir, self.targets, self.mask, self.camera_M = origin, ray_dir, targets, mask, camera_M
         self.image_size = image_size  # (resy, resx) when the rays are whole scanline-ordered images (lets Q1 work on pixel tiles)
+        self.tile_beams = tile_beams  # device-resident views only: losses.prepare_tile_beams of these rays (prepare_beams())
+
+    def prepare_beams(self):
+        """For a view that STAYS on the device (Data.keep_on_device): the per-tile direction intervals of its rays, computed once
+        (drt_tile_beams); every later losses.ray_loss_view on it skips the beam pass's scan of the ray directions."""
+        from .losses import prepare_tile_beams
+        if self.tile_beams is None and self.ray_dir.is_cuda:
+            self.tile_beams = prepare_tile_beams(self.origin, self.ray_dir, self.image_size)
+        return self
 
     @staticmethod
     def from_reference_view(view, image_size=None):

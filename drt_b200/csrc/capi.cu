@@ -689,10 +689,50 @@ int drt_ray_loss_grad_rec(const double* out_ori, const double* out_dir, const do
     return DRT_OK;
 }
 
+// signature word of prepared tile beams: pixels per image and the tile shape (wavefront.cuh: TileBeams)
+static int beam_sig(const TileMap& tm) { return (int)(((unsigned)tm.img_hw << 3) | (unsigned)tm.tw_log2); }
+
+int64_t drt_tile_beams_floats(int64_t N) { return N < 0 ? 0 : 12 * ((N + 31) / 32 + 1); }
+
+int drt_tile_beams(const double* origin, int64_t rays_per_origin, const double* dir, int64_t N, int32_t image_w, int32_t image_h,
+                   float* beams, void* stream)
+{
+    if (N < 0 || N > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_tile_beams: N must be in [0, 2^31)");
+    if (rays_per_origin < 1 || rays_per_origin > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_tile_beams: rays_per_origin must be >= 1");
+    if (image_w < 0 || image_h < 0) return fail(DRT_ERR_INVALID, "drt_tile_beams: negative image size");
+    if (!beams || (N > 0 && (!origin || !dir))) return fail(DRT_ERR_INVALID, "drt_tile_beams: null buffer");
+    if (((uintptr_t)beams & 15u) != 0) return fail(DRT_ERR_INVALID, "drt_tile_beams: beams must be 16-byte aligned");
+    int dev;
+    CU(device_of(beams, &dev));
+    DeviceGuard g(dev);
+    const TileMap tm = tile_map(image_w, image_h, N, false);
+    if ((int64_t)tm.img_hw >= (1 << 28)) return fail(DRT_ERR_INVALID, "drt_tile_beams: image too large");
+#if DRT_FUSE_R
+    const LossEntryJob job{RaySrc{origin, dir, (int)rays_per_origin}, nullptr, nullptr, tm, 0, RefractCtx{nullptr, nullptr, 0.0, 0.0}, Park{nullptr, 0}};
+#else
+    const LossEntryJob job{RaySrc{origin, dir, (int)rays_per_origin}, nullptr, nullptr, tm, 0};
+#endif
+    const int64_t n_tiles = (N + 31) / 32;
+    tile_beams_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>(blocks_for(n_tiles, 128), 148 * 16)), 128, 0, (cudaStream_t)stream>>>(
+        job, (int)N, reinterpret_cast<float4*>(beams), n_tiles + 1, beam_sig(tm));
+    ++g_launches;
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
 int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64_t rays_per_origin, const double* dir,
                       int64_t N, double ext_ior, double int_ior, int target_mode, const double* screen, const uint8_t* valid,
                       const int32_t* tgt_idx, const double* tgt_xyz, int64_t n_tgt, int32_t image_w, int32_t image_h,
                       double* loss_sum, double* grad_V, int32_t* n_paths, void* ev_after_fwd, void* stream)
+{
+    return drt_ray_loss_step_beams(b, V64, origin, rays_per_origin, dir, N, ext_ior, int_ior, target_mode, screen, valid, tgt_idx, tgt_xyz,
+                                   n_tgt, image_w, image_h, nullptr, loss_sum, grad_V, n_paths, ev_after_fwd, stream);
+}
+
+int drt_ray_loss_step_beams(drt_bvh* b, const double* V64, const double* origin, int64_t rays_per_origin, const double* dir,
+                            int64_t N, double ext_ior, double int_ior, int target_mode, const double* screen, const uint8_t* valid,
+                            const int32_t* tgt_idx, const double* tgt_xyz, int64_t n_tgt, int32_t image_w, int32_t image_h,
+                            const float* tile_beams, double* loss_sum, double* grad_V, int32_t* n_paths, void* ev_after_fwd, void* stream)
 {
     if (!b) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: null handle");
     if (!b->built) return fail(DRT_ERR_STATE, "drt_ray_loss_step: no mesh has been set (update_mesh first)");
@@ -701,6 +741,7 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
     if (target_mode != 0 && target_mode != 1) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: target_mode must be 0 (dense) or 1 (sparse)");
     if (n_tgt < 0 || n_tgt > 2147483647LL) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: n_tgt must be in [0, 2^31)");
     if (image_w < 0 || image_h < 0) return fail(DRT_ERR_INVALID, "drt_ray_loss_step: negative image size");
+    if (((uintptr_t)tile_beams & 15u) != 0) return fail(DRT_ERR_INVALID, "drt_ray_loss_step_beams: tile_beams must be 16-byte aligned");
     DeviceGuard g(b->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (n_paths) CU(cudaMemsetAsync(n_paths, 0, sizeof(int32_t), st));
@@ -819,7 +860,9 @@ int drt_ray_loss_step(drt_bvh* b, const double* V64, const double* origin, int64
             // one beam per LANE needs 32 tiles per fetch: small batches get a smaller grid (>= 2 fetches per warp), not fewer tiles
             const int tpb = tuning().beam_tpb ? tuning().beam_tpb : 32;
             const int bg = (int)std::max<int64_t>(1, std::min<int64_t>(l.pg, ((l.n + 31) / 32 + (int64_t)tpb * 8 - 1) / ((int64_t)tpb * 8)));
-            ls_beam_kernel<<<bg, 128, 0, ls[k]>>>(b->view(), j1, (int)l.n, l.ctl + 0, tpb, tuning().beam_steps, tiles, n_tiles);
+            // intervals prepared by drt_tile_beams for exactly this batch (the kernel checks the signature: N, image, tile shape)
+            const TileBeams prepared{reinterpret_cast<const float4*>(tile_beams), (N + 31) / 32 + 1, (int)N, j1.tiles.img_w, beam_sig(j1.tiles)};
+            ls_beam_kernel<<<bg, 128, 0, ls[k]>>>(b->view(), j1, (int)l.n, l.ctl + 0, tpb, tuning().beam_steps, tiles, n_tiles, prepared);
             ++g_launches;
             DRT_LAUNCH_Q(ls_q1_tiles_kernel, l.pg, ls[k], b->view(), j1, (int)l.n, tiles, n_tiles, l.ctl + 6, pol[0]);
         } else

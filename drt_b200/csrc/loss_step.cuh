@@ -206,9 +206,26 @@ __global__ void __launch_bounds__(128, MINB) ls_q1_kernel(BvhView B, LossEntryJo
 
 #if DRT_QNODE
 __global__ void __launch_bounds__(128, 8) ls_beam_kernel(BvhView B, LossEntryJob job, int N, unsigned long long* work, int tpb,
-                                                         int max_steps, int2* __restrict__ tiles, int* __restrict__ n_tiles)
+                                                         int max_steps, int2* __restrict__ tiles, int* __restrict__ n_tiles,
+                                                         TileBeams prepared)
 {
-    beam_pass(B, job, N, work, tpb, max_steps, tiles, n_tiles);
+    beam_pass(B, job, N, work, tpb, max_steps, tiles, n_tiles, prepared, job.base);
+}
+
+// drt_tile_beams: the per-tile direction intervals of a ray batch, once per view set (TileBeams, wavefront.cuh).  One thread per
+// tile runs the same scan the beam pass would run in every step; thread 0 writes the signature.
+__global__ void __launch_bounds__(128) tile_beams_kernel(LossEntryJob job, int N, float4* __restrict__ out, int64_t stride, int sig_hw_tw)
+{
+    const int64_t n_tiles = ((int64_t)N + 31) >> 5;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_tiles; t += (int64_t)gridDim.x * blockDim.x) {
+        const TileBeam b = tile_scan(job, (int)(t << 5), N);
+        const unsigned fl = (b.has_rays ? 1u : 0u) | (b.shared_origin ? 2u : 0u);
+        out[1 + t] = make_float4(b.dmn[0], b.dmn[1], b.dmn[2], __uint_as_float(fl));
+        out[stride + 1 + t] = make_float4(b.dmx[0], b.dmx[1], b.dmx[2], b.ox);
+        out[2 * stride + 1 + t] = make_float4(b.oy, b.oz, 0.f, 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        out[0] = make_float4(__uint_as_float(kBeamMagic), __int_as_float(N), __int_as_float(job.tiles.img_w), __int_as_float(sig_hw_tw));
 }
 
 template <int MINB>

@@ -138,64 +138,109 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
 //      batches whose 32 tiles all survive are 30x longer than empty ones and the kernel ends in their tail) and trace its
 //      rays exactly as before (walk_vote / drain), starting at the entry point.
 // Hit ids are unchanged (the beam only removes box tests that every ray of the tile would fail).
+// The direction intervals and the common origin of ONE tile (32 work items), i.e. everything the beam test needs to know about
+// the tile's rays.  They depend on the rays only -- not on the mesh -- and DRT's view sets are fixed for a whole optimisation
+// (captured_data.py:94-108: loaded once, optim.py:95 cycles through them), so a caller may compute them ONCE per view set
+// (drt_tile_beams) and hand them to every later step instead of having the beam pass re-read all ray directions (1.19 GB per
+// step at C4 for 75 MB of intervals).
+struct TileBeam {
+    float dmn[3], dmx[3];
+    float ox, oy, oz;
+    bool has_rays, shared_origin;
+};
+
+// Prepared tile beams, structure of arrays: three float4 planes of `stride` = n_tiles + 1 entries.
+//   plane 0: (dmin.x, dmin.y, dmin.z, flags)   flags bit 0 = has rays, bit 1 = all rays start at one point and none is NaN
+//   plane 1: (dmax.x, dmax.y, dmax.z, o.x)     plane 2: (o.y, o.z, -, -)
+// Entry 0 of plane 0 is a SIGNATURE (magic, N, image width, pixels per image << 3 | log2 tile width): the beam pass uses the
+// prepared intervals only when it matches its own tile map, and scans the rays itself otherwise.
+constexpr unsigned kBeamMagic = 0x4D414542u;  // "BEAM"
+struct TileBeams {
+    const float4* __restrict__ p;  // nullptr: none prepared
+    int64_t stride;
+    int sig_n, sig_w, sig_hw_tw;  // what the signature must say
+    __device__ __forceinline__ bool usable() const
+    {
+        if (!p) return false;
+        const float4 h = __ldg(p);
+        return __float_as_uint(h.x) == kBeamMagic && __float_as_int(h.y) == sig_n && __float_as_int(h.z) == sig_w && __float_as_int(h.w) == sig_hw_tw;
+    }
+    __device__ __forceinline__ TileBeam load(int64_t tile) const
+    {
+        const float4 a = __ldg(p + 1 + tile), b = __ldg(p + stride + 1 + tile), c = __ldg(p + 2 * stride + 1 + tile);
+        const unsigned fl = __float_as_uint(a.w);
+        return TileBeam{{a.x, a.y, a.z}, {b.x, b.y, b.z}, b.w, c.x, c.y, (fl & 1u) != 0, (fl & 2u) != 0};
+    }
+};
+
+// scans the 32 rays of the tile whose first work item is `first` (read in turn: neighbouring lanes read neighbouring tiles,
+// every sector a lane touches is used up by its next loads)
+template <class Job>
+__device__ __forceinline__ TileBeam tile_scan(const Job& job, int first, int total)
+{
+    TileBeam t{{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}, 0.f, 0.f, 0.f, false, true};
+    // the 32 work items of a tile map to rays r0 + row * img_w + col (TileMap): one index computation per tile, not per ray
+    const int r0 = job.ray_of(first);
+    const int tw_log2 = job.tiles.tw_log2, tw_mask = (1 << tw_log2) - 1, row_stride = job.tiles.img_w;
+    // rays that provably read the same origin row (one row per view, captured_data.py:38) need it once per tile
+    const int r_last = row_stride ? r0 + (31 >> tw_log2) * row_stride + tw_mask : r0 + 31;
+    const bool one_row = first + 31 < total && job.same_origin_row(r0, r_last);
+    d3 o_tile = mk3(0, 0, 0);
+    if (one_row) o_tile = job.origin_of(r0);
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+        d3 o = o_tile, d;
+        if (first + j < total) {
+            const int i = row_stride ? r0 + (j >> tw_log2) * row_stride + (j & tw_mask) : r0 + j;
+            if (one_row) d = job.dir_of(i);
+            else job.load_ray(i, o, d);
+            const QRay r = cast_ray(o, d);
+            if (!t.has_rays) { t.ox = r.ox; t.oy = r.oy; t.oz = r.oz; t.has_rays = true; }
+            t.shared_origin = t.shared_origin && r.ox == t.ox && r.oy == t.oy && r.oz == t.oz;
+            t.dmn[0] = fminf(t.dmn[0], r.dx); t.dmn[1] = fminf(t.dmn[1], r.dy); t.dmn[2] = fminf(t.dmn[2], r.dz);
+            t.dmx[0] = fmaxf(t.dmx[0], r.dx); t.dmx[1] = fmaxf(t.dmx[1], r.dy); t.dmx[2] = fmaxf(t.dmx[2], r.dz);
+            if (!(r.dx == r.dx && r.dy == r.dy && r.dz == r.dz)) t.shared_origin = false;  // a NaN direction: no beam
+        }
+    }
+    return t;
+}
+
 template <class Job>
 __device__ __forceinline__ void beam_pass(const BvhView& B, Job& job, int total, unsigned long long* work, int tpb, int max_steps,
-                                          int2* __restrict__ tiles, int* __restrict__ n_tiles)
+                                          int2* __restrict__ tiles, int* __restrict__ n_tiles, TileBeams prepared = TileBeams{nullptr, 0, 0, 0, 0},
+                                          int base_item = 0)
 {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     int stack[kStackDepth];
+    const bool use_prepared = prepared.usable();
     for (;;) {
         unsigned long long base64 = 0;
         if (lane == 0) base64 = atomicAdd(work, (unsigned long long)(32 * tpb));
         base64 = __shfl_sync(FULL, base64, 0);
         if (base64 >= (unsigned long long)total) break;
         const int base = (int)base64;
-        // ---- A: direction intervals and the common origin of the lane's own tile (32 rays, read in turn: neighbouring lanes
-        //      read neighbouring tiles, every sector a lane touches is used up by its next loads) ------------------------
-        float dmn[3] = {INFINITY, INFINITY, INFINITY}, dmx[3] = {-INFINITY, -INFINITY, -INFINITY};
-        float box = 0.f, boy = 0.f, boz = 0.f;
-        bool has_rays = false, shared_origin = true;
-        if ((int)lane < tpb) {
+        // ---- A: direction intervals and the common origin of the lane's own tile: prepared by the caller, or scanned here ----
+        TileBeam tb{{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, 0.f, 0.f, 0.f, false, true};
+        if ((int)lane < tpb && base + 32 * (int)lane < total) {
             const int first = base + 32 * (int)lane;
-            // the 32 work items of a tile map to rays r0 + row * img_w + col (TileMap): one index computation per tile, not per ray
-            const int r0 = job.ray_of(first);
-            const int tw_log2 = job.tiles.tw_log2, tw_mask = (1 << tw_log2) - 1, row_stride = job.tiles.img_w;
-            // rays that provably read the same origin row (one row per view, captured_data.py:38) need it once per tile
-            const int r_last = row_stride ? r0 + (31 >> tw_log2) * row_stride + tw_mask : r0 + 31;
-            const bool one_row = first + 31 < total && job.same_origin_row(r0, r_last);
-            d3 o_tile = mk3(0, 0, 0);
-            if (one_row) o_tile = job.origin_of(r0);
-#pragma unroll 4
-            for (int j = 0; j < 32; ++j) {
-                d3 o = o_tile, d;
-                if (first + j < total) {
-                    const int i = row_stride ? r0 + (j >> tw_log2) * row_stride + (j & tw_mask) : r0 + j;
-                    if (one_row) d = job.dir_of(i);
-                    else job.load_ray(i, o, d);
-                    const QRay r = cast_ray(o, d);
-                    if (!has_rays) { box = r.ox; boy = r.oy; boz = r.oz; has_rays = true; }
-                    shared_origin = shared_origin && r.ox == box && r.oy == boy && r.oz == boz;
-                    dmn[0] = fminf(dmn[0], r.dx); dmn[1] = fminf(dmn[1], r.dy); dmn[2] = fminf(dmn[2], r.dz);
-                    dmx[0] = fmaxf(dmx[0], r.dx); dmx[1] = fmaxf(dmx[1], r.dy); dmx[2] = fmaxf(dmx[2], r.dz);
-                    if (!(r.dx == r.dx && r.dy == r.dy && r.dz == r.dz)) shared_origin = false;  // a NaN direction: no beam
-                }
-            }
+            if (use_prepared) tb = prepared.load(((int64_t)first + base_item) >> 5);
+            else tb = tile_scan(job, first, total);
         }
         // ---- B: one beam per lane ------------------------------------------------------------------------------
         bool keep = false;
         int entry = 0;
-        if (has_rays) {
+        if (tb.has_rays) {
             keep = true;  // different origins inside the tile: no beam, every ray from the root
-            if (shared_origin && B.nTris > 0) {
-                const BeamQ bq = beam_setup(B, box, boy, boz, dmn, dmx);
+            if (tb.shared_origin && B.nTris > 0) {
+                const BeamQ bq = beam_setup(B, tb.ox, tb.oy, tb.oz, tb.dmn, tb.dmx);
                 keep = beam_walk(B, bq, stack, entry, max_steps);
             }
         }
         const int slot = warp_append<>(n_tiles, keep);
         if (slot >= 0) tiles[slot] = make_int2(base + 32 * (int)lane, entry);
         if (Job::kMissWrites) {  // culled tiles: their rays retire as misses (dense outputs are zero-filled)
-            unsigned culled = __ballot_sync(FULL, has_rays && !keep);
+            unsigned culled = __ballot_sync(FULL, tb.has_rays && !keep);
             while (culled) {
                 const int t = __ffs(culled) - 1;
                 culled &= culled - 1;

@@ -122,9 +122,10 @@ class RayLossStep(torch.autograd.Function):
     """loss and d loss/d vertices from ONE drt_ray_loss_step call (six launches, no dense per-ray output)."""
 
     @staticmethod
-    def forward(ctx, vertices, origin, rpo, ray_dir, screen, valid, targets, mesh, int_ior, ext_ior, n_paths, ev_after_fwd, image_size):
+    def forward(ctx, vertices, origin, rpo, ray_dir, screen, valid, targets, mesh, int_ior, ext_ior, n_paths, ev_after_fwd, image_size,
+                tile_beams=None):
         dev = mesh.device
-        optix.check_on(dev, vertices=vertices, origin=origin, ray_dir=ray_dir, screen=screen, valid=valid, n_paths=n_paths,
+        optix.check_on(dev, vertices=vertices, origin=origin, ray_dir=ray_dir, screen=screen, valid=valid, n_paths=n_paths, tile_beams=tile_beams,
                        **({"targets.idx": targets.idx, "targets.xyz": targets.xyz} if targets is not None else {}))
         V = vertices.detach().contiguous()
         o, d = origin.detach(), ray_dir.detach().contiguous()
@@ -148,15 +149,18 @@ class RayLossStep(torch.autograd.Function):
                 if valid.shape != (n,):
                     raise ValueError("valid must be [N]")
                 val = valid.to(torch.bool).contiguous()
+        if tile_beams is not None and (tile_beams.dtype != torch.float32 or not tile_beams.is_contiguous()
+                                       or tile_beams.numel() != _lib.load().drt_tile_beams_floats(n)):
+            raise ValueError("tile_beams must be the float32 buffer prepare_tile_beams returned for this batch")
         need_grad = ctx.needs_input_grad[0]
         loss = torch.zeros(1, dtype=torch.float64, device=dev)
         grad_V = torch.zeros_like(V) if need_grad else None
-        _lib.call("drt_ray_loss_step", mesh._h, _ptr(V), _ptr(o), int(rpo), _ptr(d), n, float(ext_ior), float(int_ior), mode,
+        _lib.call("drt_ray_loss_step_beams", mesh._h, _ptr(V), _ptr(o), int(rpo), _ptr(d), n, float(ext_ior), float(int_ior), mode,
                   _ptr(scr), _ptr(val), _ptr(idx), _ptr(xyz), n_tgt, int(image_size[1]) if image_size else 0,
-                  int(image_size[0]) if image_size else 0, _ptr(loss), _ptr(grad_V), _ptr(n_paths),
+                  int(image_size[0]) if image_size else 0, _ptr(tile_beams), _ptr(loss), _ptr(grad_V), _ptr(n_paths),
                   C.c_void_p(ev_after_fwd or 0), optix._stream_ptr(dev))
         st = torch.cuda.current_stream(dev)
-        for t in (V, o, d, scr, val, idx, xyz):  # consumed asynchronously on the stream
+        for t in (V, o, d, scr, val, idx, xyz, tile_beams):  # consumed asynchronously on the stream
             if t is not None:
                 t.record_stream(st)
         ctx.save_for_backward(grad_V)
@@ -165,27 +169,52 @@ class RayLossStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss):
         (grad_V,) = ctx.saved_tensors
-        return (grad_V * g_loss if grad_V is not None else None,) + (None,) * 12
+        return (grad_V * g_loss if grad_V is not None else None,) + (None,) * 13
 
 
-def ray_loss(scene, origin, ray_dir, screen=None, valid=None, targets=None, n_paths=None, ev_after_fwd=None, image_size=None):
+def prepare_tile_beams(origin, ray_dir, image_size=None):
+    """Per-tile direction intervals of a ray batch (drt_tile_beams), to be computed ONCE per view set and passed to every later
+    `ray_loss(..., tile_beams=...)` on the same rays: the view sets of DRT are fixed for a whole optimisation
+    (captured_data.py:94-108, optim.py:95), and what the entry query's beam culling needs from the rays does not depend on the
+    mesh.  `origin`, `ray_dir`, `image_size` exactly as they will be given to `ray_loss`.  -> float32 device tensor (1.5 B/ray)."""
+    rows, rpo = origin_rows(origin, ray_dir.shape[0])
+    d = ray_dir.detach().contiguous()
+    optix.check_on(d.device, origin=rows, ray_dir=d)
+    if not d.is_cuda or rows.dtype != torch.float64 or d.dtype != torch.float64 or d.dim() != 2 or d.shape[1] != 3:
+        raise TypeError("prepare_tile_beams needs float64 CUDA rays [N,3]")
+    n = d.shape[0]
+    beams = torch.empty(_lib.load().drt_tile_beams_floats(n), dtype=torch.float32, device=d.device)
+    with torch.cuda.device(d.device):
+        _lib.call("drt_tile_beams", _ptr(rows), int(rpo), _ptr(d), n, int(image_size[1]) if image_size else 0,
+                  int(image_size[0]) if image_size else 0, _ptr(beams), optix._stream_ptr(d.device))
+    st = torch.cuda.current_stream(d.device)
+    rows.record_stream(st)
+    d.record_stream(st)
+    return beams
+
+
+def ray_loss(scene, origin, ray_dir, screen=None, valid=None, targets=None, n_paths=None, ev_after_fwd=None, image_size=None,
+             tile_beams=None):
     """sum over valid & traced rays of || out_dir - normalize(screen - out_ori) ||^2  (optim.py:96-106).
 
     Either the reference's dense pair (`screen` [N,3], `valid` [N] or None) or `targets` = SparseTargets.
     `origin`: [N,3], expanded/[1,3] (one origin for all rays) or [r,3] with r | N (ray i starts at row i // (N/r)).
     `n_paths`: optional int32[1] device tensor receiving the number of valid two-bounce paths.
     `image_size` = (resy, resx): optional hint that the rays are whole images in scanline order (captured_data.py:26-31);
-    the entry query then works on 32-pixel tiles (4x8, else 8x4).  Same results either way."""
+    the entry query then works on 32-pixel tiles (4x8, else 8x4).  Same results either way.
+    `tile_beams`: optional buffer from `prepare_tile_beams(origin, ray_dir, image_size)` for these very rays (fixed view sets):
+    the beam pass then skips its scan of all ray directions.  Same results either way."""
     if (screen is None) == (targets is None):
         raise ValueError("give either screen (+valid) or targets")
     rows, rpo = origin_rows(origin, ray_dir.shape[0])
     return RayLossStep.apply(scene.vertices, rows, rpo, ray_dir, screen, valid, targets, scene.optix_mesh, _R.intIOR, _R.extIOR,
-                             n_paths, ev_after_fwd, image_size)
+                             n_paths, ev_after_fwd, image_size, tile_beams)
 
 
 def ray_loss_view(scene, view):
     """`view` = captured_data.CompactView (one origin row, ray_dir, sparse targets) on the scene's device."""
-    return ray_loss(scene, view.origin, view.ray_dir, targets=view.targets, image_size=getattr(view, "image_size", None))
+    return ray_loss(scene, view.origin, view.ray_dir, targets=view.targets, image_size=getattr(view, "image_size", None),
+                    tile_beams=getattr(view, "tile_beams", None))
 
 
 class SilhouetteLoss(torch.autograd.Function):

@@ -192,6 +192,27 @@ DRT_API int drt_ray_loss_step(drt_bvh* bvh, const double* V64, const double* ori
                       int32_t image_h, double* loss_sum, double* grad_V, int32_t* n_paths, void* ev_after_fwd, void* stream);
 
 /*
+ * Per-tile direction intervals of a ray batch, prepared ONCE per view set.  DRT's view sets are fixed for a whole optimisation
+ * (captured_data.py:94-108 loads them once, optim.py:95 cycles through them), and what the beam-culling pass of the entry query
+ * needs to know about the 32 rays of a pixel tile -- their common origin and the per-axis interval of their float32 directions
+ * (DiffRender.py:387-388 casts) -- depends on the rays only, never on the mesh.  drt_tile_beams computes it for a batch laid out
+ * exactly as drt_ray_loss_step will receive it (same origin / rays_per_origin / dir / N / image_w / image_h) into
+ * beams float32[drt_tile_beams_floats(N)] (device memory, 16-byte aligned; 1.5 B per ray); drt_ray_loss_step_beams is
+ * drt_ray_loss_step with that buffer: its beam pass then reads 75 MB of intervals instead of re-reading 1.19 GB of ray directions
+ * per step (C4).  tile_beams = NULL is drt_ray_loss_step.  The buffer carries a signature (N, image size, tile shape); a buffer
+ * that does not match the call is ignored and the rays are scanned as usual.  It is the caller's promise that origin and dir still
+ * hold the values the buffer was prepared from.  Results are identical either way (same intervals, same culling).
+ */
+DRT_API int64_t drt_tile_beams_floats(int64_t N);
+DRT_API int drt_tile_beams(const double* origin, int64_t rays_per_origin, const double* dir, int64_t N, int32_t image_w, int32_t image_h,
+                   float* beams, void* stream);
+DRT_API int drt_ray_loss_step_beams(drt_bvh* bvh, const double* V64, const double* origin, int64_t rays_per_origin,
+                      const double* dir, int64_t N, double ext_ior, double int_ior, int target_mode, const double* screen,
+                      const uint8_t* valid, const int32_t* tgt_idx, const double* tgt_xyz, int64_t n_tgt, int32_t image_w,
+                      int32_t image_h, const float* tile_beams, double* loss_sum, double* grad_V, int32_t* n_paths,
+                      void* ev_after_fwd, void* stream);
+
+/*
  * Replaces captured_data.generate_ray -- captured_data.py:23-40 (the pinhole sets build their rays
  * with it, captured_data.py:149): pixel (x, y, 1), x fastest, through K_inverse float64[3,3] and
  * R_inverse float64[4,4] (camera-to-world, row-major) -> dir float64[resy*resx,3] normalised and

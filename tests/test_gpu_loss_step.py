@@ -90,6 +90,18 @@ def test_loss_step_vs_oracle_and_every_input_layout(cuda_device, mesh, res, ks):
     }
     if len(ks) == 1:
         layouts["expanded origin"] = run(per_view.expand(len(d), 3), targets=sparse)
+    # per-tile direction intervals prepared once for the (fixed) rays instead of being re-derived in every step: same culling
+    counts = {}
+    for name, origin, size in (("tiles, origin per view", per_view, res), ("strips, origin per view", per_view, None), ("tiles, origin per ray", o, res)):
+        beams = losses.prepare_tile_beams(origin, d, size)
+        layouts["prepared beams, " + name] = run(origin, targets=sparse, image_size=size, tile_beams=beams)
+        counts[name] = sc.optix_mesh.last_counts()
+        run(origin, targets=sparse, image_size=size)
+        assert sc.optix_mesh.last_counts() == counts[name], name
+        assert 0 < counts[name]["tiles_kept"] < counts[name]["tiles"]
+    # a buffer prepared for another tile map does not match the call's signature: ignored, the rays are scanned as usual
+    layouts["stale beams are ignored"] = run(per_view, targets=sparse, image_size=res, tile_beams=losses.prepare_tile_beams(per_view, d, None))
+    assert sc.optix_mesh.last_counts() == counts["tiles, origin per view"]
     for name, (loss, g, n_paths) in layouts.items():
         assert n_paths == ref_paths, name
         assert abs(loss - ref_loss) <= 1e-12 * abs(ref_loss), (name, loss, ref_loss)
@@ -234,3 +246,29 @@ def test_loss_step_cabi_errors(cuda_device):
     assert lib.drt_ray_loss_step(h, p(V), p(t), 1, p(t), 8, 1.0, 1.5, 0, p(t), None, None, None, 0, 0, 0, p(t), None, None, None, st) == 0
     assert lib.drt_generate_rays(-1, 4, p(t), p(t), p(t), p(t), st) == 1
     torch.cuda.synchronize()
+
+
+def test_tile_beams_hold_the_direction_intervals_of_each_tile(cuda_device):
+    """drt_tile_beams against numpy: per 4x8 pixel tile the min / max of the float32-cast directions and the common origin."""
+    from drt_b200 import losses
+    v, _ = load_mesh("hand_vh")
+    res = (64, 96)
+    o_cpu, d_cpu, cam_o = _views_of(v, res, (5, 50))
+    d = d_cpu.to(cuda_device)
+    per_view = torch.cat(cam_o).to(cuda_device)
+    n_tiles = len(d) // 32
+    b = losses.prepare_tile_beams(per_view, d, res).cpu().numpy().reshape(3, n_tiles + 1, 4)
+    hdr = b[0, 0].view(np.int32)
+    assert hdr[0] == 0x4D414542 and hdr[1] == len(d) and hdr[2] == res[1] and hdr[3] == ((res[0] * res[1]) << 3 | 2)
+    d32 = d_cpu.numpy().astype(np.float32).reshape(2, res[0] // 8, 8, res[1] // 4, 4, 3)
+    assert np.array_equal(b[0, 1:, :3], d32.min(axis=(2, 4)).reshape(-1, 3))
+    assert np.array_equal(b[1, 1:, :3], d32.max(axis=(2, 4)).reshape(-1, 3))
+    assert (b[0, 1:, 3].view(np.uint32) == 3).all()                       # has rays | one origin
+    o32 = np.repeat(torch.cat(cam_o).numpy().astype(np.float32), n_tiles // 2, axis=0)
+    assert np.array_equal(np.stack([b[1, 1:, 3], b[2, 1:, 0], b[2, 1:, 1]], axis=1), o32)
+    # rays with their own origin rows that differ inside a tile: no beam for those tiles
+    o_var = o_cpu.clone()
+    o_var[::977] += 0.25
+    bv = losses.prepare_tile_beams(o_var.to(cuda_device), d, res).cpu().numpy().reshape(3, n_tiles + 1, 4)
+    flags = bv[0, 1:, 3].view(np.uint32)
+    assert (flags == 1).sum() > 0 and ((flags == 1) | (flags == 3)).all()
