@@ -546,6 +546,7 @@ def run_b200(args):
     # graph and replayed: same kernels, same arguments (the library's scratch and torch's graph pool are static), no Python or
     # launch overhead between them.  The all-reduce stays outside (its epoch is a kernel argument that changes every call).
     probe = None
+    direct_route = 0 < n_local <= int(_lib.load().drt_tuning_get(b"direct_max_rays"))  # drt_ray_loss_step picks the one-thread-per-path forward
     use_graph = args.loss_path == "step" and n_local > 0 and (args.graph == "on" or (args.graph == "auto" and n_local <= 8_000_000))
     graph = None
     graph_launches = 0
@@ -1014,7 +1015,7 @@ def run_b200(args):
                         "issue_frac = executed lane-instructions/s over 148 SM x 4 schedulers x 32 lanes x SM clock is the efficiency figure; "
                         "`frac` is the no-cache HBM model of SURVEY.md 8(d), kept for continuity",
             }
-            roof = {"bound": "hbm", "kernel": ("forward wavefront = ls_q1+ls_r1+ls_q2+ls_r2+ls_q3 (first five launches of drt_ray_loss_step)" if args.loss_path == "step" else "fused forward = wf_q1+wf_r1+wf_q2+wf_r2+wf_q3 (one drt_trace_fwd call)"), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            roof = {"bound": "hbm", "kernel": ("ls_direct_kernel (whole forward path per thread; small batch)" if args.loss_path == "step" and direct_route else "forward wavefront = ls_q1+ls_r1+ls_q2+ls_r2+ls_q3 (first five launches of drt_ray_loss_step)" if args.loss_path == "step" else "fused forward = wf_q1+wf_r1+wf_q2+wf_r2+wf_q3 (one drt_trace_fwd call)"), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "dram_gbs_actual": (traffic / (t_fwd_ms * 1e-3) / 1e9) if traffic else None,
                     "peak_source": peak_src, "bytes_per_ray_fwd": b_fwd, "bytes_per_ray_total": b_tot,
                     "kernel_ms": t_fwd_ms, "rays_per_launch": n_total // world,
@@ -1030,6 +1031,8 @@ def run_b200(args):
                        "allreduce": ("none" if world == 1 else "peer-memory one-shot kernel (drt_comm_*)" if ddist.peer_allreduce(1, dev) is not None else "torch.distributed/NCCL"),
                        "bvh": "refit each step" if args.refit else "full LBVH rebuild each step", "loss_path": args.loss_path,
                        "launch": "one CUDA graph replay per step" if graph is not None else "stream launches",
+                       "fwd_route": ("one thread per path (ls_direct_kernel): batch <= direct_max_rays" if args.loss_path == "step" and direct_route
+                                     else "staged wavefront (beam, Q1, R1, Q2, R2, Q3)"),
                        "l2": "inputs larger than L2 (%.1f GB of rays per step per GPU)" % (n_local * 48 / 1e9),
                        "tile_beams": ("per-tile direction intervals of the fixed view set prepared once at load time (drt_tile_beams, 1.5 B/ray resident)"
                                       if beams is not None else "derived from the rays inside every step"),

@@ -14,6 +14,8 @@ SIGNATURES = {
     "drt_version": (C.c_int, []),
     "drt_last_error": (C.c_char_p, []),
     "drt_kernel_launches": (C.c_uint64, []),
+    "drt_tuning_set": (C.c_int, [C.c_char_p, C.c_longlong]),
+    "drt_tuning_get": (C.c_longlong, [C.c_char_p]),
     "drt_bvh_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "drt_bvh_destroy": (C.c_int, [_vp]),
     "drt_bvh_build": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),

@@ -71,6 +71,7 @@ struct Tuning {
     int lanes = 2;  // DRT_LANES=1: drt_ray_loss_step on the caller's stream only (no split); =2..4 forces that many lanes at any size
     bool lanes_forced = false;
     int64_t lanes_max_rays = 16 << 20;  // default: two lanes for batches up to 16 M rays
+    int64_t direct_max_rays = 3 << 19;  // DRT_DIRECT_MAX / drt_tuning_set("direct_max_rays"): measured on B200 -- C2 (262 k rays) step 0.372 -> 0.264 ms, one 960x720 view (691 k) 0.43 -> 0.37, one 960x1280 view on mouse_vh (1.23 M) 0.61 -> 0.50, three 960x720 views (2.1 M) 0.675 -> 0.746: batches up to this many rays run the one-thread-per-path forward (ls_direct_kernel)
     int beam_steps = 1 << 30;  // DRT_BEAM_STEPS: node steps after which an undecided beam is kept
     int beam_tpb = 0;  // DRT_BEAM_TPB = 1..32 forces the tiles a warp takes per work fetch (default: by batch size)
     int thresh = 32;
@@ -117,6 +118,8 @@ struct Tuning {
         if (bm2 && !strcmp(bm2, "0")) beam = false;
         const char* ln = getenv("DRT_LANES");
         if (ln && atoi(ln) >= 1 && atoi(ln) <= 4) { lanes = atoi(ln); lanes_forced = lanes >= 2; }
+        const char* dm = getenv("DRT_DIRECT_MAX");
+        if (dm && atoll(dm) >= 0) direct_max_rays = atoll(dm);
         const char* bs = getenv("DRT_BEAM_STEPS");
         if (bs && atoi(bs) >= 1) beam_steps = atoi(bs);
         const char* tp = getenv("DRT_BEAM_TPB");
@@ -128,11 +131,12 @@ struct Tuning {
         if (minb != 4 && minb != 6 && minb != 7 && minb != 8 && minb != 10) minb = 8;
     }
 };
-const Tuning& tuning()
+Tuning& tuning_mut()
 {
     static Tuning t;
     return t;
 }
+const Tuning& tuning() { return tuning_mut(); }
 
 }  // namespace
 
@@ -384,7 +388,20 @@ int build_common(drt_bvh* b, const int32_t* F, int nF, const float* V32, const d
 
 extern "C" {
 
-int drt_version(void) { return 1001; }
+int drt_version(void) { return 1002; }
+
+int drt_tuning_set(const char* key, long long value)
+{
+    if (!key || value < 0) return fail(DRT_ERR_INVALID, "drt_tuning_set: null key or negative value");
+    if (!strcmp(key, "direct_max_rays")) { tuning_mut().direct_max_rays = value; return DRT_OK; }
+    return fail(DRT_ERR_INVALID, "drt_tuning_set: unknown key");
+}
+
+long long drt_tuning_get(const char* key)
+{
+    if (key && !strcmp(key, "direct_max_rays")) return tuning().direct_max_rays;
+    return -1;
+}
 
 unsigned long long drt_kernel_launches(void) { return g_launches; }
 
@@ -779,7 +796,7 @@ int drt_ray_loss_step_beams(drt_bvh* b, const double* V64, const double* origin,
     // tails only matter when a stage lasts a few hundred microseconds, so large batches stay on one lane
     int n_lanes = 1;
     int64_t cut[kMaxLanes + 1] = {0, N, N, N, N};  // lane k = rays [cut[k], cut[k+1])
-    if (tuning().lanes >= 2 && b->lane_stream[0] && N >= (1 << 17) && (N <= tuning().lanes_max_rays || tuning().lanes_forced)) {
+    if (tuning().lanes >= 2 && b->lane_stream[0] && N >= (1 << 17) && N > tuning().direct_max_rays && (N <= tuning().lanes_max_rays || tuning().lanes_forced)) {
         // split at image boundaries when there are enough images, else at 32-ray batches (= pixel tiles: the item -> ray map
         // below is the one of the WHOLE batch, so a lane may start in the middle of an image)
         const int64_t unit = (img > 0 && N % img == 0 && N / img >= tuning().lanes) ? img : 32;
@@ -840,8 +857,17 @@ int drt_ray_loss_step_beams(drt_bvh* b, const double* V64, const double* origin,
         else KERNEL<4><<<PG, 128, 0, ST>>>(__VA_ARGS__);                                    \
     } while (0)
     const bool beam = DRT_QNODE && tuning().beam && (pol[0] & 0xff) == 32;
+    // small batches: the whole forward path of a ray in one thread (ls_direct_kernel), then the usual loss/backward kernel
+    const bool direct = n_lanes == 1 && N <= tuning().direct_max_rays;
+    if (direct) {
+        Lane& l = lane[0];
+        const int dg = (int)std::min<int64_t>(blocks_for(l.n, 128), (int64_t)b->sm_count * 16);
+        ls_direct_kernel<<<dg, 128, 0, st>>>(b->view(), V64, rays, tile_map(image_w, image_h, N, false), (int)N, ext_ior, int_ior, tgt, l.S,
+                                             l.countL, l.countM, l.countS);
+        g_launches -= 4;  // direct + loss/backward = 2 launches instead of the 6 counted below
+    }
     // stage by stage, lane by lane: the launches of the two lanes alternate so that neither stream waits for the host
-    for (int k = 0; k < n_lanes; ++k) {  // Q1: entry query
+    for (int k = 0; k < n_lanes && !direct; ++k) {  // Q1: entry query
         Lane& l = lane[k];
         // whole images of image_w x image_h pixels that a 32-pixel tile shape divides: a warp's batch becomes a pixel tile
 #if DRT_FUSE_R
@@ -869,7 +895,7 @@ int drt_ray_loss_step_beams(drt_bvh* b, const double* V64, const double* origin,
 #endif
         DRT_LAUNCH_Q(ls_q1_kernel, l.pg, ls[k], b->view(), j1, (int)l.n, l.ctl + 0, pol[0]);
     }
-    for (int k = 0; k < n_lanes; ++k) {  // R1 + Q2: refraction at the entry hit, exit query
+    for (int k = 0; k < n_lanes && !direct; ++k) {  // R1 + Q2: refraction at the entry hit, exit query
         Lane& l = lane[k];
 #if DRT_FUSE_R
         LossExitJob j2{l.park, l.L, RefractCtx{V64, b->F, ext_ior, int_ior}, tgt, l.M, l.countM};
@@ -879,7 +905,7 @@ int drt_ray_loss_step_beams(drt_bvh* b, const double* V64, const double* origin,
 #endif
         DRT_LAUNCH_Q(ls_q2_kernel, l.pg, ls[k], b->view(), j2, l.countL, l.ctl + 1, pol[1]);
     }
-    for (int k = 0; k < n_lanes; ++k) {  // R2 + Q3: refraction at the exit hit (+ target lookup), occlusion query
+    for (int k = 0; k < n_lanes && !direct; ++k) {  // R2 + Q3: refraction at the exit hit (+ target lookup), occlusion query
         Lane& l = lane[k];
 #if !DRT_FUSE_R
         ls_r2_kernel<<<l.dgrid, 128, 0, ls[k]>>>(b->view(), V64, ext_ior, int_ior, l.L, l.countL, l.park, tgt, l.M, l.countM);

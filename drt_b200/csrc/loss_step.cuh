@@ -352,6 +352,50 @@ __global__ void __launch_bounds__(128, MINB) ls_q3_kernel(BvhView B, LossOcclusi
     persistent_query<true>(B, job, *countM, work, policy, stack);
 }
 
+// ---- the whole forward path of a ray in ONE thread (small batches) --------------------------------------
+// One view per iteration is how the reference is used (optim.py:95), i.e. 10^5 .. 10^6 rays per call: the seven stage
+// launches above then cost more in launch ramps and per-stage tails (a stage cannot end before its longest ray) than the
+// divergence they remove.  Here a thread runs entry query -> refraction -> exit query -> refraction -> occlusion query for
+// its ray (same traversal, same float64 chain: identical hit ids and exit rays) and appends the valid path to S, which
+// ls_loss_bwd_kernel consumes as usual: 2 launches per step instead of 8.  countL / countM only feed the stage statistics.
+#ifndef DRT_DIRECT_MINB
+#define DRT_DIRECT_MINB 1
+#endif
+__global__ void __launch_bounds__(128, DRT_DIRECT_MINB) ls_direct_kernel(BvhView B, const double* __restrict__ V64, RaySrc rays, TileMap tiles, int N,
+                                                        double ext_ior, double int_ior, TargetSrc tgt, int4* __restrict__ S,
+                                                        int* __restrict__ countL, int* __restrict__ countM, int* __restrict__ countS)
+{
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < N; item += gridDim.x * blockDim.x) {
+        const int i = tiles.ray_of(item);
+        const d3 o = rays.o(i), d = rays.d(i);
+        int id1, id2 = -1, id3 = -1;
+        double t;
+        bool alive = false;
+        traverse<false>(B, cast_ray(o, d), t, id1);
+        if (id1 >= 0) {
+            HitRec h;
+            d3 a0, a1, a2, o1, d1, o2, d2;
+            load_tri64(B, V64, id1, a0, a1, a2);
+            hit_forward(h, o, d, a0, a1, a2, ext_ior, int_ior, o1, d1);
+            if (!h.tir) {
+                traverse<false>(B, cast_ray(o1, d1), t, id2);
+                if (id2 >= 0) {
+                    load_tri64(B, V64, id2, a0, a1, a2);
+                    hit_forward(h, o1, d1, a0, a1, a2, ext_ior, int_ior, o2, d2);
+                    if (!h.tir) {
+                        alive = true;
+                        traverse<true>(B, cast_ray(o2, d2), t, id3);
+                    }
+                }
+            }
+        }
+        warp_append<>(countL, id1 >= 0);
+        warp_append<>(countM, alive);
+        const int slot = warp_append<>(countS, alive && id3 < 0);
+        if (slot >= 0) S[slot] = make_int4(i, id1, id2, tgt.find(i));
+    }
+}
+
 // ---- loss + backward over the valid paths -------------------------------------------------------------
 // One thread per valid path: re-evaluates the two hits in float64 (bit-identical to R1/R2), forms
 //   target = normalize(screen - out_ori),  diff = out_dir - target,  loss += |diff|^2,  g_out_dir = 2 diff

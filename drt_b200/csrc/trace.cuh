@@ -579,10 +579,30 @@ __device__ __forceinline__ bool can_step(int node, int nd)
 #endif
 }
 
+#ifndef DRT_LEAF_FALL
+#define DRT_LEAF_FALL 0
+#endif
 // one node step or one leaf push (the caller checked can_step)
 template <bool WIDE, class S>
 __device__ __forceinline__ void advance(const BvhView& B, const RayQ& q, float tmax, int& node, S& stack, int& sp, int& nd)
 {
+#if DRT_LEAF_FALL
+    // a leaf is queued and the popped node is stepped in the SAME iteration: the queueing is a short divergent prefix instead
+    // of a whole loop iteration in which the lane skips the node step the rest of the warp executes
+    if (node < 0) {
+        stack.leaf_put(nd, node);
+        prefetch_tri(B, node);
+        ++nd;
+        node = stack.pop_or(sp, kDone);
+    }
+    if (node >= 0) {
+#if DRT_QNODE && DRT_BVH4
+        node = WIDE ? node_step4(B, q, tmax, node, stack, sp, nd) : node_step(B, q, tmax, node, stack, sp, nd);
+#else
+        node = node_step(B, q, tmax, node, stack, sp, nd);
+#endif
+    }
+#else
     if (node >= 0) {
 #if DRT_QNODE && DRT_BVH4
         node = WIDE ? node_step4(B, q, tmax, node, stack, sp, nd) : node_step(B, q, tmax, node, stack, sp, nd);
@@ -595,6 +615,7 @@ __device__ __forceinline__ void advance(const BvhView& B, const RayQ& q, float t
         ++nd;
         node = stack.pop_or(sp, kDone);
     }
+#endif
 }
 
 // walk until the stack is exhausted or the lane is blocked by its full leaf queue
@@ -642,6 +663,101 @@ __device__ __forceinline__ bool drain(const BvhView& B, const RayQ& q, S& stack,
         if (ANY && hit) { nd = 0; return true; }
     }
     return false;
+}
+
+// DRT_COOP_DRAIN = 1: the queued leaves of a WARP are tested cooperatively.  drain() runs as many rounds as the longest
+// queue of the warp, with fewer lanes in each (ncu, r02: the float64 triangle tests are 20 % of the exit query and run at
+// 11 -> 3 active lanes).  Here every queued (ray, leaf) pair of the warp is one task; the tasks are numbered level by level
+// (first leaf of every lane, then second, ...) through a per-warp table in shared memory, lane w tests task w with the ray
+// fetched from its owner by shuffles, and the owner folds the results of its own tasks back into (t_best, id_best) -- the same
+// lexicographic minimum over the same float64 tests, so hit ids and distances are unchanged; a warp with 11 + 7 + 3 queued
+// leaves does ONE round of 21 lanes instead of three rounds of 11, 7 and 3.  All 32 lanes must call it (converged).
+#ifndef DRT_COOP_DRAIN
+#define DRT_COOP_DRAIN 1
+#endif
+struct CoopScratch {
+    double t[32];
+    int task[32];
+    int id[32];
+};
+
+template <bool ANY, class S>
+__device__ __forceinline__ bool drain_coop(const BvhView& B, const RayQ& q, S& stack, int& nd, double& t_best, int& id_best, float& tmax)
+{
+    const unsigned FULL = 0xffffffffu;
+    unsigned m[kDefer];
+#pragma unroll
+    for (int j = 0; j < kDefer; ++j) m[j] = __ballot_sync(FULL, nd > j);
+    if (m[0] == 0u) return false;
+    const bool own = kDefer < 2 || m[1] == 0u;  // at most one leaf per lane: every lane tests its own, no table
+    __shared__ CoopScratch scratch_all[kQueryBlock / 32];
+    CoopScratch& sc = scratch_all[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    int k[kDefer], leaf[kDefer];  // task index of this lane's j-th leaf (-1: none)
+    int total = 0;
+#pragma unroll
+    for (int j = 0; j < kDefer; ++j) {
+        k[j] = nd > j ? total + __popc(m[j] & lt) : -1;
+        leaf[j] = nd > j ? stack.leaf_get(j) : -1;
+        total += __popc(m[j]);
+    }
+    bool found = false;
+    double tb = t_best;
+    int ib = id_best;
+    for (int r = 0; r < (own ? 1 : total); r += 32) {
+        bool work = nd > 0;
+        int tri = ~leaf[0];
+        QRay ray = q.r;
+        if (!own) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < kDefer; ++j)
+                if (k[j] >= r && k[j] < r + 32) sc.task[k[j] - r] = ((~leaf[j]) << 5) | (int)lane;
+            __syncwarp();
+            work = (int)lane < total - r;
+            const int tk = work ? sc.task[lane] : (int)lane;
+            const int owner = tk & 31;
+            tri = tk >> 5;
+            ray.ox = __shfl_sync(FULL, q.r.ox, owner); ray.oy = __shfl_sync(FULL, q.r.oy, owner); ray.oz = __shfl_sync(FULL, q.r.oz, owner);
+            ray.dx = __shfl_sync(FULL, q.r.dx, owner); ray.dy = __shfl_sync(FULL, q.r.dy, owner); ray.dz = __shfl_sync(FULL, q.r.dz, owner);
+        }
+        double t = 0.0;
+        int id = -1;
+        if (work) {
+            const double2* p = B.tris + (size_t)tri * kTriD2;
+            const double2 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
+            if (query_tri(mk3((double)ray.ox, (double)ray.oy, (double)ray.oz), mk3((double)ray.dx, (double)ray.dy, (double)ray.dz),
+                          mk3(w0.x, w0.y, w1.x), mk3(w1.y, w2.x, w2.y), mk3(w3.x, w3.y, w4.x), t))
+                id = (int)__double_as_longlong(w4.y);
+        }
+        if (own) {
+            if (id >= 0) {
+                found = true;
+                if (t < tb || (t == tb && id < ib)) { tb = t; ib = id; }
+            }
+        } else {
+            if (work) { sc.t[lane] = t; sc.id[lane] = id; }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < kDefer; ++j)
+                if (k[j] >= r && k[j] < r + 32) {
+                    const int id_j = sc.id[k[j] - r];
+                    if (id_j >= 0) {
+                        const double t_j = sc.t[k[j] - r];
+                        found = true;
+                        if (t_j < tb || (t_j == tb && id_j < ib)) { tb = t_j; ib = id_j; }
+                    }
+                }
+        }
+    }
+    nd = 0;
+    if (ib != id_best || tb != t_best) {
+        t_best = tb;
+        id_best = ib;
+        tmax = tmax_of(q, tb);
+    }
+    return ANY && found;
 }
 
 // Exact closest hit (ANY = false) or first hit found (ANY = true; only hit/no-hit is meaningful,

@@ -105,7 +105,7 @@ __device__ __forceinline__ void persistent_query(const BvhView& B, Job& job, int
         for (;;) {
             if (vote) walk_vote<kWideQueries>(B, q, tmax, node, stack, sp, nd, vote);
             else walk<kWideQueries>(B, q, tmax, node, stack, sp, nd);
-            if (drain<ANY>(B, q, stack, nd, t_best, id_best, tmax)) { node = kDone; stack.reset(sp); }
+            if (DRT_COOP_DRAIN ? drain_coop<ANY>(B, q, stack, nd, t_best, id_best, tmax) : drain<ANY>(B, q, stack, nd, t_best, id_best, tmax)) { node = kDone; stack.reset(sp); }
             unsigned fin = __ballot_sync(FULL, item >= 0 && node == kDone);
             if (__popc(fin) >= need) break;
         }
@@ -281,7 +281,8 @@ __device__ __forceinline__ void entry_query_tiles(const BvhView& B, Job& job, in
         for (;;) {
             if (vote) walk_vote<kWideQueries>(B, q, tmax, node, stack, sp, nd, vote);
             else walk<kWideQueries>(B, q, tmax, node, stack, sp, nd);
-            drain<false>(B, q, stack, nd, t_best, id_best, tmax);
+            if (DRT_COOP_DRAIN) drain_coop<false>(B, q, stack, nd, t_best, id_best, tmax);
+            else drain<false>(B, q, stack, nd, t_best, id_best, tmax);
             if (!__any_sync(FULL, node != kDone)) break;
         }
         if (act) job.retire(item, id_best, t_best);

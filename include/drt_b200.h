@@ -295,6 +295,17 @@ DRT_API int drt_comm_destroy(drt_comm* comm);
 /* Text of the last error on this thread ("" if none).  Never NULL. */
 DRT_API const char* drt_last_error(void);
 
+/*
+ * Runtime switch of a scheduling choice (results never depend on one).  No counterpart in the reference.
+ *   "direct_max_rays"  drt_ray_loss_step batches of up to this many rays run the whole forward path of a ray in one
+ *                      thread (2 launches per step) instead of the staged wavefront (8 launches): the reference renders ONE
+ *                      view per iteration (optim.py:95), i.e. 10^5 .. 10^6 rays per call, where the stage launches and their
+ *                      tails cost more than the divergence they remove.  Default 3 << 19 = 1 572 864 (env DRT_DIRECT_MAX); 0 = never.
+ * Returns DRT_ERR_INVALID for an unknown key or a negative value.  Not thread-safe against concurrent calls of the library.
+ */
+DRT_API int drt_tuning_set(const char* key, long long value);
+DRT_API long long drt_tuning_get(const char* key);
+
 /* Number of kernels this library has launched in this process (monotonic; for bench accounting). */
 DRT_API unsigned long long drt_kernel_launches(void);
 

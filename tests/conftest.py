@@ -59,3 +59,15 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(params=["staged", "direct"])
+def fwd_route(request, cuda_device):
+    """drt_ray_loss_step has two forward routes chosen by batch size (drt_tuning_set "direct_max_rays"): the staged wavefront the
+    benchmark times and the one-thread-per-path kernel for single views.  Tests that use this fixture run on BOTH at every size."""
+    from drt_b200 import _lib
+    lib = _lib.load()
+    old = lib.drt_tuning_get(b"direct_max_rays")
+    _lib.call("drt_tuning_set", b"direct_max_rays", 0 if request.param == "staged" else 2_000_000_000)
+    yield request.param
+    _lib.call("drt_tuning_set", b"direct_max_rays", old)

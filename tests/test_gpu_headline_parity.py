@@ -14,7 +14,7 @@ import torch
 from conftest import grad_rel_err
 from oracle import oracle
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("fwd_route")]
 
 
 def _cfg(name):
