@@ -71,7 +71,7 @@ struct Tuning {
     int lanes = 2;  // DRT_LANES=1: drt_ray_loss_step on the caller's stream only (no split); =2..4 forces that many lanes at any size
     bool lanes_forced = false;
     int64_t lanes_max_rays = 16 << 20;  // default: two lanes for batches up to 16 M rays
-    int64_t direct_max_rays = 3 << 19;  // DRT_DIRECT_MAX / drt_tuning_set("direct_max_rays"): measured on B200 -- C2 (262 k rays) step 0.372 -> 0.264 ms, one 960x720 view (691 k) 0.43 -> 0.37, one 960x1280 view on mouse_vh (1.23 M) 0.61 -> 0.50, three 960x720 views (2.1 M) 0.675 -> 0.746: batches up to this many rays run the one-thread-per-path forward (ls_direct_kernel)
+    int64_t direct_max_rays = 1250000;  // DRT_DIRECT_MAX / drt_tuning_set("direct_max_rays"): measured on B200 -- C2 (262 k rays) step 0.342 -> 0.261 ms, one 960x720 view (691 k) 0.43 -> 0.365 (C4 mesh) / 0.395 -> 0.364 (C3), one 960x1280 view on mouse_vh (1.23 M) 0.547 -> 0.499, two 960x720 views (1.38 M) 0.510 -> 0.555, three (2.1 M) 0.59 -> 0.73: batches up to this many rays run the one-thread-per-path forward (ls_direct_kernel)
     int beam_steps = 1 << 30;  // DRT_BEAM_STEPS: node steps after which an undecided beam is kept
     int beam_tpb = 0;  // DRT_BEAM_TPB = 1..32 forces the tiles a warp takes per work fetch (default: by batch size)
     int thresh = 32;

@@ -300,7 +300,7 @@ DRT_API const char* drt_last_error(void);
  *   "direct_max_rays"  drt_ray_loss_step batches of up to this many rays run the whole forward path of a ray in one
  *                      thread (2 launches per step) instead of the staged wavefront (8 launches): the reference renders ONE
  *                      view per iteration (optim.py:95), i.e. 10^5 .. 10^6 rays per call, where the stage launches and their
- *                      tails cost more than the divergence they remove.  Default 3 << 19 = 1 572 864 (env DRT_DIRECT_MAX); 0 = never.
+ *                      tails cost more than the divergence they remove.  Default 1 250 000 (env DRT_DIRECT_MAX); 0 = never.
  * Returns DRT_ERR_INVALID for an unknown key or a negative value.  Not thread-safe against concurrent calls of the library.
  */
 DRT_API int drt_tuning_set(const char* key, long long value);
