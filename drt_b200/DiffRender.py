@@ -98,6 +98,105 @@ class RefractTrace(torch.autograd.Function):
         return grad_V, None, None, None, None, None
 
 
+class RefractTraceSmooth(torch.autograd.Function):
+    """OPTIONAL non-parity mode: (vertices, normals, origin, ray_dir) -> (out_ori, out_dir, mask) with the shading normal
+    interpolated from the vertex normals (the code the reference keeps commented out, DiffRender.py:107-114).
+    forward = drt_trace_fwd_smooth, backward = drt_trace_bwd_smooth: d/d vertices (through the hit distances) and
+    d/d normals (the Jacobian w.r.t. the interpolated normals), both scatter-added per vertex."""
+
+    @staticmethod
+    def forward(ctx, vertices, normals, origin, ray_dir, mesh, int_ior, ext_ior):
+        dev = mesh.device
+        optix.check_on(dev, vertices=vertices, normals=normals, origin=origin, ray_dir=ray_dir)
+        if any(t.dtype != torch.float64 for t in (vertices, normals, origin, ray_dir)):
+            raise TypeError("render_transparent works in float64 like the reference (DiffRender.py:19)")
+        V, VN = vertices.detach().contiguous(), normals.detach().contiguous()
+        o, d = origin.detach().contiguous(), ray_dir.detach().contiguous()
+        if o.dim() != 2 or o.shape[1] != 3 or o.shape != d.shape:
+            raise ValueError(f"origin/ray_dir must both be [N,3], got {tuple(o.shape)} and {tuple(d.shape)}")
+        if V.shape[0] != mesh.n_verts or VN.shape != V.shape:
+            raise ValueError(f"vertices / normals must be [{mesh.n_verts},3], got {tuple(V.shape)} and {tuple(VN.shape)}")
+        n = o.shape[0]
+        out_ori = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        out_dir = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        mask = torch.empty((n, 3), dtype=torch.bool, device=dev)
+        rec = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+        rec_count = torch.empty(1, dtype=torch.int32, device=dev)
+        _lib.call("drt_trace_fwd_smooth", mesh._h, _ptr(V), _ptr(VN), _ptr(o), _ptr(d), n, float(ext_ior), float(int_ior), _ptr(out_ori),
+                  _ptr(out_dir), _ptr(mask), _ptr(rec), _ptr(rec_count), optix._stream_ptr(dev))
+        ctx.mesh = mesh
+        ctx.iors = (float(ext_ior), float(int_ior))
+        ctx.save_for_backward(V, VN, o, d, rec, rec_count)
+        ctx.mark_non_differentiable(mask)
+        ctx.set_materialize_grads(False)
+        return out_ori, out_dir, mask
+
+    @staticmethod
+    def backward(ctx, g_ori, g_dir, _g_mask):
+        V, VN, o, d, rec, rec_count = ctx.saved_tensors
+        grad_V, grad_VN = torch.zeros_like(V), torch.zeros_like(VN)
+        if g_ori is None and g_dir is None:
+            return grad_V, grad_VN, None, None, None, None, None
+        if g_dir is None:
+            g_dir = torch.zeros_like(o)
+        g_dir = g_dir.contiguous()
+        g_ori = None if g_ori is None else g_ori.contiguous()
+        mesh = ctx.mesh
+        optix.check_on(mesh.device, grad_out_dir=g_dir, grad_out_ori=g_ori)
+        _lib.call("drt_trace_bwd_smooth", mesh._h, _ptr(V), _ptr(VN), _ptr(o), _ptr(d), o.shape[0], ctx.iors[0], ctx.iors[1], _ptr(rec),
+                  _ptr(rec_count), _ptr(g_ori), _ptr(g_dir), _ptr(grad_V), _ptr(grad_VN), optix._stream_ptr(mesh.device))
+        return grad_V, grad_VN, None, None, None, None, None
+
+
+class PlaneHit(torch.autograd.Function):
+    """OPTIONAL: (out_ori, out_dir, mask) -> points where the exit rays of the valid paths meet a background plane
+    (drt_plane_hit / drt_plane_hit_bwd).  Not part of the reference's loss."""
+
+    @staticmethod
+    def forward(ctx, out_ori, out_dir, mask, plane_point, plane_normal):
+        dev = out_ori.device
+        o, d = out_ori.detach().contiguous(), out_dir.detach().contiguous()
+        m = mask.contiguous()
+        if m.dim() != 2 or m.shape[1] != 3 or o.shape != d.shape or o.shape[0] != m.shape[0] or o.dtype != torch.float64 or not o.is_cuda:
+            raise ValueError("plane_hit takes render_transparent's outputs: float64 [N,3] CUDA out_ori / out_dir and bool [N,3] mask")
+        plane = (C.c_double * 6)(*[float(x) for x in plane_point], *[float(x) for x in plane_normal])
+        n = o.shape[0]
+        pts = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        front = torch.empty(n, dtype=torch.bool, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("drt_plane_hit", _ptr(o), _ptr(d), _ptr(m), n, plane, _ptr(pts), _ptr(front), optix._stream_ptr(dev))
+        ctx.plane = plane
+        ctx.save_for_backward(o, d, m)
+        ctx.mark_non_differentiable(front)
+        return pts, front
+
+    @staticmethod
+    def backward(ctx, g_pts, _g_front):
+        o, d, m = ctx.saved_tensors
+        g_o, g_d = torch.empty_like(o), torch.empty_like(d)
+        with torch.cuda.device(o.device):
+            _lib.call("drt_plane_hit_bwd", _ptr(o), _ptr(d), _ptr(m), o.shape[0], ctx.plane, _ptr(g_pts.contiguous()), _ptr(g_o), _ptr(g_d),
+                      optix._stream_ptr(o.device))
+        return g_o, g_d, None, None, None
+
+
+def vertex_normals(vertices, faces):
+    """Scene.init_VN (DiffRender.py:319-336) with JIT_corner_angles (:165-187): vertex normal = normalised sum of the
+    adjacent unit face normals weighted by the (detached) corner angle; differentiable w.r.t. `vertices` through the face
+    normals, like the reference (`triangles` is not detached there, the weights are)."""
+    tri = vertices[faces]
+    u, v, w = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0], tri[:, 2] - tri[:, 1]
+    face_n = torch.linalg.cross(u, v, dim=1)
+    face_n = face_n / face_n.norm(dim=1, keepdim=True)
+    with torch.no_grad():
+        un, vn, wn = (x / x.norm(dim=1, keepdim=True) for x in (u, v, w))
+        a0 = torch.acos((un * vn).sum(1).clamp(-1, 1))
+        a1 = torch.acos((-un * wn).sum(1).clamp(-1, 1))
+        angles = torch.stack([a0, a1, np.pi - a0 - a1], dim=1)                  # [F,3]
+    vert_n = torch.zeros_like(vertices).index_add(0, faces.reshape(-1), (angles.unsqueeze(2) * face_n.unsqueeze(1)).reshape(-1, 3))
+    return vert_n / vert_n.norm(dim=1, keepdim=True)
+
+
 class Scene:
     """Same public surface as the reference Scene (DiffRender.py:298-546) for the methods optim.py
     drives: ctor, update_mesh, update_verticex, render_transparent, render_mask, optix_intersect,
@@ -107,6 +206,9 @@ class Scene:
         self.cuda_device = cuda_device
         self.optix_mesh = optix.optix_mesh(cuda_device)
         self.refit = False  # True: update_verticex refits the BVH instead of rebuilding it
+        # OPTIONAL non-parity mode: shade with normals interpolated from the vertex normals instead of the
+        # flat face normal the reference uses (DiffRender.py:103-104 live, :107-114 commented out)
+        self.smooth_normals = False
         self._mesh, self._mesh_dirty = None, False
         if mesh_path is not None:
             self.update_mesh(mesh_path)
@@ -177,7 +279,20 @@ class Scene:
     # DiffRender.py:420-432
     def render_transparent(self, origin, ray_dir):
         self.optix_mesh.set_image_size(resy, resx)  # module globals, assigned by the caller like optim.py:179-180
+        if self.smooth_normals:
+            return RefractTraceSmooth.apply(self.vertices, self.init_VN(), origin, ray_dir, self.optix_mesh, intIOR, extIOR)
         return RefractTrace.apply(self.vertices, origin, ray_dir, self.optix_mesh, intIOR, extIOR)
+
+    # DiffRender.py:319-336 (dead in the reference's live path, F2/F12; only the smooth-normal mode needs it)
+    def init_VN(self):
+        self.normals = vertex_normals(self.vertices, self.faces)
+        return self.normals
+
+    def render_background(self, origin, ray_dir, plane_point, plane_normal):
+        """OPTIONAL (north-star wording, not in the reference: SURVEY.md F5): the two-bounce path followed by the
+        intersection of the exit ray with a background plane -> (points [N,3], front bool[N])."""
+        out_ori, out_dir, mask = self.render_transparent(origin, ray_dir)
+        return PlaneHit.apply(out_ori, out_dir, mask, plane_point, plane_normal)
 
     # DiffRender.py:434-438
     def render_mask(self, origin, ray_dir):

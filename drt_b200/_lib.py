@@ -28,6 +28,10 @@ SIGNATURES = {
     "drt_closest_hit": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "drt_trace_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "drt_trace_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drt_trace_fwd_smooth": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drt_trace_bwd_smooth": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "drt_plane_hit": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(_f64), _vp, _vp, _vp]),
+    "drt_plane_hit_bwd": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(_f64), _vp, _vp, _vp, _vp]),
     "drt_ray_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "drt_ray_loss_grad_rec": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "drt_ray_loss_step": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _f64, _f64, C.c_int, _vp, _vp, _vp, _vp, _i64, _i32, _i32,

@@ -8,6 +8,7 @@
 
 #include "../../include/drt_b200.h"
 #include "bvh_coop.cuh"
+#include "plane.cuh"
 #include "loss_step.cuh"
 #include "peer_allreduce.cuh"
 #include "silhouette.cuh"
@@ -561,9 +562,29 @@ int drt_closest_hit(const drt_bvh* b, const float* ray6, int64_t N, float* T, in
     return DRT_OK;
 }
 
+static int trace_fwd_impl(drt_bvh* b, const double* V64, const double* VN, const double* origin, const double* dir, int64_t N, double ext_ior,
+                          double int_ior, double* out_ori, double* out_dir, uint8_t* mask3, int32_t* rec, int32_t* rec_count,
+                          uint8_t* hit1, void* stream);
+
 int drt_trace_fwd(drt_bvh* b, const double* V64, const double* origin, const double* dir, int64_t N, double ext_ior,
                   double int_ior, double* out_ori, double* out_dir, uint8_t* mask3, int32_t* rec, int32_t* rec_count,
                   uint8_t* hit1, void* stream)
+{
+    return trace_fwd_impl(b, V64, nullptr, origin, dir, N, ext_ior, int_ior, out_ori, out_dir, mask3, rec, rec_count, hit1, stream);
+}
+
+int drt_trace_fwd_smooth(drt_bvh* b, const double* V64, const double* VN64, const double* origin, const double* dir, int64_t N,
+                         double ext_ior, double int_ior, double* out_ori, double* out_dir, uint8_t* mask3, int32_t* rec,
+                         int32_t* rec_count, void* stream)
+{
+    if (b && b->nF > 0 && N > 0 && !VN64) return fail(DRT_ERR_INVALID, "drt_trace_fwd_smooth: VN64 is null");
+    return trace_fwd_impl(b, V64, VN64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir, mask3, rec, rec_count, nullptr, stream);
+}
+
+// VN != nullptr: optional smooth-normal mode (vertex normals float64 [nV,3]); always the five-launch wavefront
+static int trace_fwd_impl(drt_bvh* b, const double* V64, const double* VN, const double* origin, const double* dir, int64_t N, double ext_ior,
+                          double int_ior, double* out_ori, double* out_dir, uint8_t* mask3, int32_t* rec, int32_t* rec_count,
+                          uint8_t* hit1, void* stream)
 {
     if (!b) return fail(DRT_ERR_INVALID, "drt_trace_fwd: null handle");
     if (!b->built) return fail(DRT_ERR_STATE, "drt_trace_fwd: no mesh has been set (update_mesh first)");
@@ -577,7 +598,7 @@ int drt_trace_fwd(drt_bvh* b, const double* V64, const double* origin, const dou
     if (!origin || !dir || !out_ori || !out_dir || !mask3) return fail(DRT_ERR_INVALID, "drt_trace_fwd: null buffer");
     if (b->nF > 0 && !V64) return fail(DRT_ERR_INVALID, "drt_trace_fwd: V64 is null");
     // small batches: the five-launch wavefront has ~0.1 ms of fixed cost, the one-launch megakernel wins below ~1 M rays
-    if (tuning().simple_fwd || (!tuning().force_wavefront && N <= kSimpleMaxRays)) {
+    if (!VN && (tuning().simple_fwd || (!tuning().force_wavefront && N <= kSimpleMaxRays))) {
         int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * 64);
         trace_fwd_kernel<<<grid, 128, 0, st>>>(b->view(), V64, origin, dir, N, ext_ior, int_ior, out_ori, out_dir, mask3,
                                                (int4*)rec, rec_count, hit1, tile_map(b->img_w, b->img_h, N, true));
@@ -599,7 +620,7 @@ int drt_trace_fwd(drt_bvh* b, const double* V64, const double* origin, const dou
                     tile_map(b->img_w, b->img_h, N, true)};
         const int minb = tuning().minb;
         const int pg = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * minb);
-        if (tuning().one_launch && b->fused_blocks_per_sm > 0) {
+        if (!VN && tuning().one_launch && b->fused_blocks_per_sm > 0) {
             // the whole wavefront as ONE cooperative launch (grid-wide barriers between the stages)
             FwdArgs fa{b->view(), V64, origin, dir, (int)N, ext_ior, int_ior, out_ori, out_dir, mask3, hit1, b->listA, b->listB,
                        (int4*)rec, rec_count, ctl, {pol[0], pol[1], pol[2]}, bulk_ok ? 1 : 0, tile_map(b->img_w, b->img_h, N, true)};
@@ -633,10 +654,10 @@ int drt_trace_fwd(drt_bvh* b, const double* V64, const double* origin, const dou
         } else
 #endif
         DRT_LAUNCH_Q(wf_q1_kernel, b->view(), j1, (int)N, ctl + 0, pol[0]);
-        wf_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, origin, dir, ext_ior, int_ior, out_ori, out_dir, mask3, b->listA, countL);
+        wf_r1_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, origin, dir, ext_ior, int_ior, out_ori, out_dir, mask3, b->listA, countL, VN);
         ExitJob j2{out_ori, out_dir, b->listA};
         DRT_LAUNCH_Q(wf_q2_kernel, b->view(), j2, countL, ctl + 1, pol[1]);
-        wf_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, out_ori, out_dir, mask3, b->listA, countL, b->listB, countM);
+        wf_r2_kernel<<<dgrid, 128, 0, st>>>(b->view(), V64, ext_ior, int_ior, out_ori, out_dir, mask3, b->listA, countL, b->listB, countM, VN);
         OcclusionJob j3{out_ori, out_dir, mask3, b->listB, (int4*)rec, rec_count};
         DRT_LAUNCH_Q(wf_q3_kernel, b->view(), j3, countM, ctl + 2, pol[2]);
 #undef DRT_LAUNCH_Q
@@ -666,6 +687,52 @@ int drt_trace_bwd(const drt_bvh* b, const double* V64, const double* origin, con
     else
         trace_bwd_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, ext_ior, int_ior, (const int4*)rec,
                                                                      rec_count, g_out_ori, g_out_dir, grad_V);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_trace_bwd_smooth(const drt_bvh* b, const double* V64, const double* VN64, const double* origin, const double* dir, int64_t N,
+                         double ext_ior, double int_ior, const int32_t* rec, const int32_t* rec_count, const double* g_out_ori,
+                         const double* g_out_dir, double* grad_V, double* grad_VN, void* stream)
+{
+    if (!b) return fail(DRT_ERR_INVALID, "drt_trace_bwd_smooth: null handle");
+    if (!b->built) return fail(DRT_ERR_STATE, "drt_trace_bwd_smooth: no mesh has been set (update_mesh first)");
+    if (N < 0) return fail(DRT_ERR_INVALID, "drt_trace_bwd_smooth: N < 0");
+    if (N == 0 || b->nF == 0) return DRT_OK;
+    if (!V64 || !VN64 || !origin || !dir || !rec || !rec_count || !g_out_dir || !grad_V || !grad_VN)
+        return fail(DRT_ERR_INVALID, "drt_trace_bwd_smooth: null buffer");
+    DeviceGuard g(b->device);
+    int grid = (int)std::min<int64_t>(blocks_for(N, 128), (int64_t)b->sm_count * DRT_BWD_MINB);
+    trace_bwd_kernel<false, true><<<grid, 128, 0, (cudaStream_t)stream>>>(b->view(), V64, origin, dir, ext_ior, int_ior, (const int4*)rec,
+                                                                       rec_count, g_out_ori, g_out_dir, grad_V, VN64, grad_VN);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_plane_hit(const double* out_ori, const double* out_dir, const uint8_t* mask3, int64_t N, const double plane[6], double* pts,
+                  uint8_t* front, void* stream)
+{
+    if (N < 0) return fail(DRT_ERR_INVALID, "drt_plane_hit: N < 0");
+    if (N == 0) return DRT_OK;
+    if (!out_ori || !out_dir || !mask3 || !plane || !pts) return fail(DRT_ERR_INVALID, "drt_plane_hit: null buffer");
+    const Plane P{plane[0], plane[1], plane[2], plane[3], plane[4], plane[5]};
+    plane_hit_kernel<<<(int)std::min<int64_t>(blocks_for(N, 256), 148 * 16), 256, 0, (cudaStream_t)stream>>>(out_ori, out_dir, mask3, N, P, pts, front);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_plane_hit_bwd(const double* out_ori, const double* out_dir, const uint8_t* mask3, int64_t N, const double plane[6],
+                      const double* g_pts, double* g_out_ori, double* g_out_dir, void* stream)
+{
+    if (N < 0) return fail(DRT_ERR_INVALID, "drt_plane_hit_bwd: N < 0");
+    if (N == 0) return DRT_OK;
+    if (!out_ori || !out_dir || !mask3 || !plane || !g_pts || !g_out_ori || !g_out_dir) return fail(DRT_ERR_INVALID, "drt_plane_hit_bwd: null buffer");
+    const Plane P{plane[0], plane[1], plane[2], plane[3], plane[4], plane[5]};
+    plane_hit_bwd_kernel<<<(int)std::min<int64_t>(blocks_for(N, 256), 148 * 16), 256, 0, (cudaStream_t)stream>>>(out_ori, out_dir, mask3, N, P, g_pts,
+                                                                                                          g_out_ori, g_out_dir);
     ++g_launches;
     CU(cudaGetLastError());
     return DRT_OK;

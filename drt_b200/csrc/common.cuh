@@ -86,16 +86,22 @@ __device__ __forceinline__ bool query_tri(d3 o, d3 d, d3 a, d3 e1, d3 e2, double
 struct HitRec {
     d3 d;            // incoming direction
     d3 a0, e1, e2;   // triangle
-    d3 N, n, np;     // N = e1 x e2, n = N/L, np = oriented normal
+    d3 N, n, np;     // N = e1 x e2, n = shading normal (N/L; smooth mode: the interpolated unit normal), np = oriented normal
     d3 wt, x;        // refracted unit direction, hit point
-    double L, t, D;  // |N|, distance, d.N
+    double L, t, D;  // |N| (smooth mode: |interpolated normal| before normalisation), distance, d.N
     double sgn, eta, c, cT, A, nw;
+    double u, v;     // barycentric coordinates of the hit (smooth mode only; detached like DiffRender.py:108-109)
     bool cT_grad;    // clamp(min=0) in Refract passes gradient
     bool tir;
 };
 
-__device__ __forceinline__ void hit_forward(HitRec& h, d3 o, d3 d, d3 a0, d3 a1, d3 a2, double ext_ior,
-                                            double int_ior, d3& o2, d3& d2)
+// SMOOTH = false is the reference's live behaviour (flat face normal, DiffRender.py:103-104).
+// SMOOTH = true is the OPTIONAL non-parity mode the reference keeps commented out (DiffRender.py:107-114): the shading normal
+// is n = normalize((1-u-v) n0 + u n1 + v n2) over the vertex normals vn[0..2] of the hit triangle, with u, v detached.
+// Everything else -- t, orientation, TIR, tan-law Refract, the 1e-5 offset -- is the same code.
+template <bool SMOOTH>
+__device__ __forceinline__ void hit_forward_t(HitRec& h, d3 o, d3 d, d3 a0, d3 a1, d3 a2, const d3* vn, double ext_ior,
+                                              double int_ior, d3& o2, d3& d2)
 {
     h.d = d; h.a0 = a0;
     h.e1 = a1 - a0; h.e2 = a2 - a0;
@@ -106,8 +112,17 @@ __device__ __forceinline__ void hit_forward(HitRec& h, d3 o, d3 d, d3 a0, d3 a1,
     d3 qvec = cross(tvec, h.e1);
     h.t = mulr(dot(h.e2, qvec), inv_det);
     h.N = cross(h.e1, h.e2);
-    h.L = __dsqrt_rn(dot(h.N, h.N));
-    h.n = divs(h.N, h.L);
+    if (SMOOTH) {
+        h.u = mulr(dot(tvec, pvec), inv_det);  // DiffRender.py:84
+        h.v = mulr(dot(d, qvec), inv_det);     // DiffRender.py:87
+        const double w0 = subr(subr(1.0, h.u), h.v);
+        const d3 nI = (vn[0] * w0 + vn[1] * h.u) + vn[2] * h.v;  // DiffRender.py:113
+        h.L = __dsqrt_rn(dot(nI, nI));
+        h.n = divs(nI, h.L);                    // DiffRender.py:114
+    } else {
+        h.L = __dsqrt_rn(dot(h.N, h.N));
+        h.n = divs(h.N, h.L);
+    }
     h.D = dot(d, h.N);
     d3 wo = -d;
     double c0 = dot(wo, h.n);
@@ -140,10 +155,18 @@ __device__ __forceinline__ void hit_forward(HitRec& h, d3 o, d3 d, d3 a0, d3 a1,
     d2 = h.wt;
 }
 
+__device__ __forceinline__ void hit_forward(HitRec& h, d3 o, d3 d, d3 a0, d3 a1, d3 a2, double ext_ior,
+                                            double int_ior, d3& o2, d3& d2)
+{
+    hit_forward_t<false>(h, o, d, a0, a1, a2, nullptr, ext_ior, int_ior, o2, d2);
+}
+
 // Reverse of hit_forward (analytic Jacobian).  (go2, gd2): gradient w.r.t. the
 // outgoing ray.  Adds the gradients of a0,a1,a2 to ga[0..2]; returns gradient w.r.t. the incoming
-// ray in (go, gd).
-__device__ __forceinline__ void hit_backward(const HitRec& h, d3 go2, d3 gd2, d3 ga[3], d3& go, d3& gd)
+// ray in (go, gd).  SMOOTH: the shading normal does not depend on the triangle's vertices but on its three vertex
+// normals -- their gradients are added to gn[0..2]; the vertices still move the hit point through t.
+template <bool SMOOTH>
+__device__ __forceinline__ void hit_backward_t(const HitRec& h, d3 go2, d3 gd2, d3 ga[3], d3* gn, d3& go, d3& gd)
 {
     d3 g_wt = gd2 + go2 * 1e-5;
     d3 g_x = go2;
@@ -159,7 +182,13 @@ __device__ __forceinline__ void hit_backward(const HitRec& h, d3 go2, d3 gd2, d3
     g_d = g_d - h.np * g_c;
     g_np = g_np - h.d * g_c;
     d3 g_n = g_np * h.sgn;
-    d3 g_N = (g_n - h.n * dot(h.n, g_n)) * __ddiv_rn(1.0, h.L);
+    d3 g_N = (g_n - h.n * dot(h.n, g_n)) * __ddiv_rn(1.0, h.L);  // SMOOTH: gradient of the un-normalised interpolated normal
+    if (SMOOTH) {
+        gn[0] = gn[0] + g_N * subr(subr(1.0, h.u), h.v);
+        gn[1] = gn[1] + g_N * h.u;
+        gn[2] = gn[2] + g_N * h.v;
+        g_N = mk3(0, 0, 0);  // N = e1 x e2 only enters through t from here on
+    }
     double k = __ddiv_rn(g_t, h.D);
     d3 g_a0 = h.N * k;
     g_o = g_o - h.N * k;
@@ -171,6 +200,11 @@ __device__ __forceinline__ void hit_backward(const HitRec& h, d3 go2, d3 gd2, d3
     ga[2] = ga[2] + g_e2;
     ga[0] = ga[0] + ((g_a0 - g_e1) - g_e2);
     go = g_o; gd = g_d;
+}
+
+__device__ __forceinline__ void hit_backward(const HitRec& h, d3 go2, d3 gd2, d3 ga[3], d3& go, d3& gd)
+{
+    hit_backward_t<false>(h, go2, gd2, ga, nullptr, go, gd);
 }
 
 }  // namespace drt

@@ -825,6 +825,15 @@ __device__ __forceinline__ void load_tri64(const BvhView& B, const double* __res
     a2 = ld3(V64 + 3 * (size_t)i2);
 }
 
+// the three vertex normals of triangle id (optional smooth-normal mode, common.cuh: hit_forward_t<true>)
+__device__ __forceinline__ void load_vn(const BvhView& B, const double* __restrict__ VN, int id, d3 vn[3])
+{
+    int i0 = __ldg(&B.F[3 * (size_t)id]), i1 = __ldg(&B.F[3 * (size_t)id + 1]), i2 = __ldg(&B.F[3 * (size_t)id + 2]);
+    vn[0] = ld3(VN + 3 * (size_t)i0);
+    vn[1] = ld3(VN + 3 * (size_t)i1);
+    vn[2] = ld3(VN + 3 * (size_t)i2);
+}
+
 __device__ __forceinline__ void write_invalid(double* __restrict__ out_ori, double* __restrict__ out_dir,
                                               uint8_t* __restrict__ mask3, int64_t i)
 {
@@ -935,13 +944,15 @@ __device__ __forceinline__ void scatter_runs(double* __restrict__ gV, const int3
 #ifndef DRT_BWD_MINB
 #define DRT_BWD_MINB 4
 #endif
-template <bool MERGE>
+// SMOOTH (optional smooth-normal mode): VN = vertex normals [nV,3], gVN receives their gradient.
+template <bool MERGE, bool SMOOTH = false>
 __global__ void __launch_bounds__(128, DRT_BWD_MINB) trace_bwd_kernel(BvhView B, const double* __restrict__ V64,
                                                         const double* __restrict__ origin, const double* __restrict__ dir,
                                                         double ext_ior, double int_ior, const int4* __restrict__ rec,
                                                         const int* __restrict__ rec_count,
                                                         const double* __restrict__ g_ori, const double* __restrict__ g_dir,
-                                                        double* __restrict__ gV)
+                                                        double* __restrict__ gV, const double* __restrict__ VN = nullptr,
+                                                        double* __restrict__ gVN = nullptr)
 {
     const int n = __ldg(rec_count);
     const int stride = gridDim.x * blockDim.x;
@@ -958,26 +969,38 @@ __global__ void __launch_bounds__(128, DRT_BWD_MINB) trace_bwd_kernel(BvhView B,
             id1 = rc.y; id2 = rc.z;
             const d3 o = ld3(origin + 3 * i), d = ld3(dir + 3 * i);
             d3 a0, a1, a2, o1, d1, o2, d2, go1, gd1, go0, gd0;
+            d3 vn[3], gn[3];
             // Only ONE hit record is live at a time (a record is ~60 doubles): hit 1 is evaluated once for its
             // outgoing ray, hit 2 is evaluated and reversed, then hit 1 is re-evaluated and reversed.
             {
                 HitRec h;
                 load_tri64(B, V64, id1, a0, a1, a2);
-                hit_forward(h, o, d, a0, a1, a2, ext_ior, int_ior, o1, d1);
+                if (SMOOTH) load_vn(B, VN, id1, vn);
+                hit_forward_t<SMOOTH>(h, o, d, a0, a1, a2, vn, ext_ior, int_ior, o1, d1);
             }
             {
                 HitRec h;
                 load_tri64(B, V64, id2, a0, a1, a2);
-                hit_forward(h, o1, d1, a0, a1, a2, ext_ior, int_ior, o2, d2);
+                if (SMOOTH) { load_vn(B, VN, id2, vn); gn[0] = gn[1] = gn[2] = z; }
+                hit_forward_t<SMOOTH>(h, o1, d1, a0, a1, a2, vn, ext_ior, int_ior, o2, d2);
                 d3 go2 = g_ori ? ld3(g_ori + 3 * i) : z;
                 d3 gd2 = ld3(g_dir + 3 * i);
-                hit_backward(h, go2, gd2, g2, go1, gd1);
+                hit_backward_t<SMOOTH>(h, go2, gd2, g2, gn, go1, gd1);
+                if (SMOOTH) {
+                    const int32_t* f = B.F + 3 * (size_t)id2;
+                    scatter3(gVN, f[0], gn[0]); scatter3(gVN, f[1], gn[1]); scatter3(gVN, f[2], gn[2]);
+                }
             }
             {
                 HitRec h;
                 load_tri64(B, V64, id1, a0, a1, a2);
-                hit_forward(h, o, d, a0, a1, a2, ext_ior, int_ior, o1, d1);
-                hit_backward(h, go1, gd1, g1, go0, gd0);
+                if (SMOOTH) { load_vn(B, VN, id1, vn); gn[0] = gn[1] = gn[2] = z; }
+                hit_forward_t<SMOOTH>(h, o, d, a0, a1, a2, vn, ext_ior, int_ior, o1, d1);
+                hit_backward_t<SMOOTH>(h, go1, gd1, g1, gn, go0, gd0);
+                if (SMOOTH) {
+                    const int32_t* f = B.F + 3 * (size_t)id1;
+                    scatter3(gVN, f[0], gn[0]); scatter3(gVN, f[1], gn[1]); scatter3(gVN, f[2], gn[2]);
+                }
             }
         }
         if (MERGE) {

@@ -403,7 +403,7 @@ __device__ __forceinline__ void r1_body(const BvhView& B, const double* __restri
                                         const double* __restrict__ origin, const double* __restrict__ dir,
                                         double ext_ior, double int_ior, double* __restrict__ out_ori,
                                         double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
-                                        int4* __restrict__ L, const int* countL)
+                                        int4* __restrict__ L, const int* countL, const double* __restrict__ VN = nullptr)
 {
     const int n = *(volatile const int*)countL;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -412,6 +412,11 @@ __device__ __forceinline__ void r1_body(const BvhView& B, const double* __restri
         HitRec h;
         d3 a0, a1, a2, o1, d1;
         load_tri64(B, V64, e.y, a0, a1, a2);
+        if (VN) {  // optional smooth-normal mode (uniform branch)
+            d3 vn[3];
+            load_vn(B, VN, e.y, vn);
+            hit_forward_t<true>(h, ld3(origin + 3 * i), ld3(dir + 3 * i), a0, a1, a2, vn, ext_ior, int_ior, o1, d1);
+        } else
         hit_forward(h, ld3(origin + 3 * i), ld3(dir + 3 * i), a0, a1, a2, ext_ior, int_ior, o1, d1);
         if (h.tir) {
             write_invalid(out_ori, out_dir, mask3, i);
@@ -427,9 +432,9 @@ __global__ void __launch_bounds__(128) wf_r1_kernel(BvhView B, const double* __r
                                                     const double* __restrict__ origin, const double* __restrict__ dir,
                                                     double ext_ior, double int_ior, double* __restrict__ out_ori,
                                                     double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
-                                                    int4* __restrict__ L, const int* __restrict__ countL)
+                                                    int4* __restrict__ L, const int* __restrict__ countL, const double* __restrict__ VN)
 {
-    r1_body(B, V64, origin, dir, ext_ior, int_ior, out_ori, out_dir, mask3, L, countL);
+    r1_body(B, V64, origin, dir, ext_ior, int_ior, out_ori, out_dir, mask3, L, countL, VN);
 }
 
 // ---- Q2 ------------------------------------------------------------------------------------------
@@ -463,7 +468,8 @@ __global__ void __launch_bounds__(128, MINB) wf_q2_kernel(BvhView B, ExitJob job
 __device__ __forceinline__ void r2_body(const BvhView& B, const double* __restrict__ V64, double ext_ior,
                                         double int_ior, double* __restrict__ out_ori,
                                         double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
-                                        const int4* L, const int* countL, int4* __restrict__ M, int* __restrict__ countM)
+                                        const int4* L, const int* countL, int4* __restrict__ M, int* __restrict__ countM,
+                                        const double* __restrict__ VN = nullptr)
 {
     const int n = *(volatile const int*)countL;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -475,6 +481,11 @@ __device__ __forceinline__ void r2_body(const BvhView& B, const double* __restri
                 HitRec h;
                 d3 a0, a1, a2, o2, d2;
                 load_tri64(B, V64, e.z, a0, a1, a2);
+                if (VN) {
+                    d3 vn[3];
+                    load_vn(B, VN, e.z, vn);
+                    hit_forward_t<true>(h, ld3(out_ori + 3 * i), ld3(out_dir + 3 * i), a0, a1, a2, vn, ext_ior, int_ior, o2, d2);
+                } else
                 hit_forward(h, ld3(out_ori + 3 * i), ld3(out_dir + 3 * i), a0, a1, a2, ext_ior, int_ior, o2, d2);
                 alive = !h.tir;
                 if (alive) {
@@ -493,9 +504,9 @@ __global__ void __launch_bounds__(128) wf_r2_kernel(BvhView B, const double* __r
                                                     double int_ior, double* __restrict__ out_ori,
                                                     double* __restrict__ out_dir, uint8_t* __restrict__ mask3,
                                                     const int4* __restrict__ L, const int* __restrict__ countL,
-                                                    int4* __restrict__ M, int* __restrict__ countM)
+                                                    int4* __restrict__ M, int* __restrict__ countM, const double* __restrict__ VN)
 {
-    r2_body(B, V64, ext_ior, int_ior, out_ori, out_dir, mask3, L, countL, M, countM);
+    r2_body(B, V64, ext_ior, int_ior, out_ori, out_dir, mask3, L, countL, M, countM, VN);
 }
 
 // ---- Q3 ------------------------------------------------------------------------------------------

@@ -296,6 +296,32 @@ DRT_API int drt_comm_destroy(drt_comm* comm);
 DRT_API const char* drt_last_error(void);
 
 /*
+ * OPTIONAL, NON-PARITY modes that BASELINE.json's north-star names and the reference does not run.
+ *
+ * Smooth-normal mode: the shading normal of a hit is n = normalize((1-u-v) n0 + u n1 + v n2) over the vertex normals of
+ * the hit triangle with u, v detached -- the interpolation the reference keeps COMMENTED OUT in JIT_Dintersect
+ * (DiffRender.py:107-114; the live code uses the flat face normal, :103-104).  VN64 = float64 [nV,3] vertex normals
+ * (Scene.init_VN, DiffRender.py:319-336, on the caller's side).  Everything else is drt_trace_fwd / drt_trace_bwd:
+ * same queries, same records; the backward additionally returns grad_VN float64 [nV,3] (accumulated, caller zeroes),
+ * the gradient w.r.t. the vertex normals, while grad_V keeps the part through the hit distances.
+ *
+ * Background plane: where the exit ray of a valid path meets the plane through plane[0..2] with normal plane[3..5]
+ * (host pointers): pts float64 [N,3] (zeros for rays without a valid path or without an intersection in front of them),
+ * front uint8 [N] (nullable) = 1 where pts is a real intersection; drt_plane_hit_bwd maps g_pts to the gradients
+ * w.r.t. out_ori / out_dir (written, not accumulated).  The reference's loss has no such step (optim.py:96-106).
+ */
+DRT_API int drt_trace_fwd_smooth(drt_bvh* bvh, const double* V64, const double* VN64, const double* origin, const double* dir, int64_t N,
+                                 double ext_ior, double int_ior, double* out_ori, double* out_dir, uint8_t* mask3, int32_t* rec,
+                                 int32_t* rec_count, void* stream);
+DRT_API int drt_trace_bwd_smooth(const drt_bvh* bvh, const double* V64, const double* VN64, const double* origin, const double* dir,
+                                 int64_t N, double ext_ior, double int_ior, const int32_t* rec, const int32_t* rec_count,
+                                 const double* g_out_ori, const double* g_out_dir, double* grad_V, double* grad_VN, void* stream);
+DRT_API int drt_plane_hit(const double* out_ori, const double* out_dir, const uint8_t* mask3, int64_t N, const double plane[6],
+                          double* pts, uint8_t* front, void* stream);
+DRT_API int drt_plane_hit_bwd(const double* out_ori, const double* out_dir, const uint8_t* mask3, int64_t N, const double plane[6],
+                              const double* g_pts, double* g_out_ori, double* g_out_dir, void* stream);
+
+/*
  * Runtime switch of a scheduling choice (results never depend on one).  No counterpart in the reference.
  *   "direct_max_rays"  drt_ray_loss_step batches of up to this many rays run the whole forward path of a ray in one
  *                      thread (2 launches per step) instead of the staged wavefront (8 launches): the reference renders ONE

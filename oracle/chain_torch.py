@@ -24,9 +24,41 @@ def _query(intersect, o, d):
     return ids.long(), T > 0
 
 
-def _surface(vertices, faces, o, d, tri_ids, int_ior, ext_ior):
+def vertex_normals(vertices, faces):
+    """Scene.init_VN + JIT_corner_angles (DiffRender.py:319-336, 165-187): sparse [V,F] matrix of detached corner angles times
+    the unit face normals, row-normalised.  Only the OPTIONAL smooth-normal mode uses it (dead in the live path, F2)."""
+    tri = vertices[faces]
+    u, v, w = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0], tri[:, 2] - tri[:, 1]
+    face_n = torch.linalg.cross(u, v, dim=1)
+    face_n = face_n / face_n.norm(dim=1, keepdim=True)
+    un, vn, wn = (x / x.norm(dim=1, keepdim=True) for x in (u, v, w))
+    ang = torch.empty_like(tri[:, :, 0])
+    ang[:, 0] = torch.acos(_dot(un, vn).clamp(-1, 1))
+    ang[:, 1] = torch.acos(_dot(-un, wn).clamp(-1, 1))
+    ang[:, 2] = torch.pi - ang[:, 0] - ang[:, 1]
+    row = faces.reshape(-1)
+    col = torch.arange(len(faces), device=faces.device).unsqueeze(1).expand(-1, 3).reshape(-1)
+    M = torch.sparse_coo_tensor(torch.stack((row, col)), ang.detach().reshape(-1), (len(vertices), len(faces)))
+    vert_n = torch.sparse.mm(M, face_n)
+    return vert_n / vert_n.norm(dim=1, keepdim=True)
+
+
+def plane_hit(out_ori, out_dir, mask, plane_point, plane_normal):
+    """OPTIONAL background-plane step (not in the reference, SURVEY.md F5): x = o + s d with s = ((p0 - o).n)/(d.n);
+    zeros where the path is invalid, the ray is parallel to the plane or the plane is behind it."""
+    p0 = torch.as_tensor(plane_point, dtype=out_ori.dtype, device=out_ori.device)
+    n = torch.as_tensor(plane_normal, dtype=out_ori.dtype, device=out_ori.device)
+    dn = out_dir @ n
+    ok = mask[:, 0] & (dn != 0)
+    s = ((p0 - out_ori) @ n) / torch.where(ok, dn, torch.ones_like(dn))
+    ok = ok & (s > 0)
+    pts = torch.where(ok.unsqueeze(1), out_ori + s.unsqueeze(1) * out_dir, torch.zeros_like(out_ori))
+    return pts, ok
+
+
+def _surface(vertices, faces, o, d, tri_ids, int_ior, ext_ior, normals=None):
     """JIT_Dintersect + refract_ray for rays that hit (DiffRender.py:64-121, 503-535).
-    -> (keep mask, new origin, new direction)"""
+    -> (keep mask, new origin, new direction).  normals != None: the commented-out interpolation of :107-114."""
     tri = vertices[faces[tri_ids]]                      # [n,3,3] gather: the differentiable link to the vertices
     a0, a1, a2 = tri[:, 0], tri[:, 1], tri[:, 2]
     e1, e2 = a1 - a0, a2 - a0
@@ -36,6 +68,12 @@ def _surface(vertices, faces, o, d, tri_ids, int_ior, ext_ior):
     t = _dot(e2, qvec) * inv_det
     n = torch.linalg.cross(e1, e2, dim=1)
     n = n / n.norm(dim=1, keepdim=True)                 # flat face normal (:103-104)
+    if normals is not None:                             # :107-114 as written there (u, v detached)
+        u = (_dot(o - a0, pvec) * inv_det).detach()
+        v = (_dot(d, qvec) * inv_det).detach()
+        nn = normals[faces[tri_ids]]
+        n = (1 - u - v).reshape((-1, 1)) * nn[:, 0] + u.reshape((-1, 1)) * nn[:, 1] + v.reshape((-1, 1)) * nn[:, 2]
+        n = n / n.norm(p=2, dim=1, keepdim=True)
     wo = -d
     cos_i = _dot(wo, n).clamp(-1, 1)
     entering = cos_i > 0
@@ -57,15 +95,15 @@ def _surface(vertices, faces, o, d, tri_ids, int_ior, ext_ior):
     return keep, new_o, w
 
 
-def render_transparent(vertices, faces, origin, ray_dir, intersect, int_ior, ext_ior=EXT_IOR):
-    """(out_ori, out_dir, mask[N,3]) with autograd history back to `vertices`."""
+def render_transparent(vertices, faces, origin, ray_dir, intersect, int_ior, ext_ior=EXT_IOR, normals=None):
+    """(out_ori, out_dir, mask[N,3]) with autograd history back to `vertices` (and `normals` in the optional smooth mode)."""
     n = origin.shape[0]
     idx = torch.arange(n, device=origin.device)
     o, d = origin, ray_dir
     for _ in range(2):                                   # trace2 (:537-546)
         ids, hit = _query(intersect, o, d)
         idx, o, d, ids = idx[hit], o[hit], d[hit], ids[hit]
-        keep, o, d = _surface(vertices, faces, o, d, ids, int_ior, ext_ior)
+        keep, o, d = _surface(vertices, faces, o, d, ids, int_ior, ext_ior, normals)
         idx, o, d = idx[keep], o[keep], d[keep]
     _, hit = _query(intersect, o, d)                     # third query: any further surface rejects the path (:425-427)
     idx, o, d = idx[~hit], o[~hit], d[~hit]

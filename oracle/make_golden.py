@@ -119,6 +119,23 @@ def silhouette_case():
     print(f"silhouette: {len(sil)} silhouette edges, {len(index)} samples in view, |grad|max {s.vertices.grad.abs().max():.3g}")
 
 
+def vertex_normals_case():
+    """Scene.init_VN (DiffRender.py:319-336) of the unmodified reference on hand_vh: the vertex normals and the gradient of a
+    seeded linear functional of them w.r.t. the vertices -- pins oracle/chain_torch.vertex_normals and
+    drt_b200.DiffRender.vertex_normals (the input of the optional smooth-normal mode)."""
+    R = ref_harness.load_reference()
+    v, f = plyio.read_ply(os.path.join(ref_harness.REF_ROOT, "data", "hand_vh.ply"))
+    s = ref_harness.make_scene(v, f, INT_IOR)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        s.init_VN()
+        w = torch.tensor(np.random.default_rng(21).standard_normal(s.normals.shape))
+        (s.normals * w).sum().backward()
+    np.savez_compressed(os.path.join(GOLD, "vertex_normals_hand_vh.npz"), normals=s.normals.detach().numpy(), weights=w.numpy(),
+                        grad_V=s.vertices.grad.numpy())
+    print(f"vertex normals: {tuple(s.normals.shape)}, |grad|max {s.vertices.grad.abs().max():.3g}")
+
+
 def view_rays(v, resy, resx, k, n_views=72):
     cams = views.turntable_cameras(v, resy, resx, n_views)
     _, _, R_inv, K_inv = cams[k]
@@ -132,6 +149,7 @@ def main():
     save_meshes()
     kat_functions()
     silhouette_case()
+    vertex_normals_case()
     # App. B tetrahedron (5 rays, one of them a miss)
     v, f = meshgen.tetrahedron()
     o = np.array([(0.6, 0.7, 9), (0.9, 0.5, 9), (0.4, 1.1, 9), (1.2, 0.3, 9), (3.9, 3.9, 9)], float)
