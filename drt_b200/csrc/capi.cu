@@ -50,7 +50,7 @@ int ensure(T*& p, size_t& cap, size_t need)
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
-constexpr int kWorkSlots = 64;
+constexpr int kWorkSlots = 256;
 constexpr int64_t kSimpleMaxRays = 1 << 20;
 // rays per vertex above which the backward kernels merge equal-triangle runs in the warp before their atomics
 // (C3, 10 760 rays per vertex: 1.28 -> 0.85 ms; C4, 1 980: 0.57 -> 0.55 ms with tile-ordered records)
@@ -69,6 +69,7 @@ struct Tuning {
     bool bulk = true;  // DRT_BULK_ZERO=0 disables the TMA bulk zero-fill of missed rays (A/B switch)
     bool coop_build = false;  // DRT_COOP_BUILD=1: the LBVH build as ONE cooperative launch (bvh_coop.cuh) -- measured SLOWER on B200 (0.208 vs 0.170 ms at 50 k triangles: 15 grid-wide barriers at ~5 us each and L2-only reads cost more than 18 launch boundaries), kept as a tested option
     bool beam = true;  // DRT_BEAM=0: entry query without beam culling of whole pixel tiles (A/B switch)
+    int lanes_big = 4;  // lanes of batches above lanes_max_rays (DRT_LANES_BIG; 1 = none)
     int lanes = 2;  // DRT_LANES=1: drt_ray_loss_step on the caller's stream only (no split); =2..4 forces that many lanes at any size
     bool lanes_forced = false;
     int64_t lanes_max_rays = 16 << 20;  // default: two lanes for batches up to 16 M rays
@@ -118,9 +119,11 @@ struct Tuning {
         const char* bm2 = getenv("DRT_BEAM");
         if (bm2 && !strcmp(bm2, "0")) beam = false;
         const char* ln = getenv("DRT_LANES");
-        if (ln && atoi(ln) >= 1 && atoi(ln) <= 4) { lanes = atoi(ln); lanes_forced = lanes >= 2; }
+        if (ln && atoi(ln) >= 1 && atoi(ln) <= 8) { lanes = atoi(ln); lanes_forced = lanes >= 2; }
         const char* dm = getenv("DRT_DIRECT_MAX");
         if (dm && atoll(dm) >= 0) direct_max_rays = atoll(dm);
+        const char* lb = getenv("DRT_LANES_BIG");
+        if (lb && atoi(lb) >= 1 && atoi(lb) <= 8) lanes_big = atoi(lb);
         const char* bs = getenv("DRT_BEAM_STEPS");
         if (bs && atoi(bs) >= 1) beam_steps = atoi(bs);
         const char* tp = getenv("DRT_BEAM_TPB");
@@ -166,9 +169,9 @@ struct drt_bvh {
     int4* listS = nullptr;     size_t capLS = 0; // loss step: (ray, tri1, tri2, target slot) of the valid paths; before Q1: the beam pass's tile list
     int* tbucket = nullptr;    size_t capTb = 0; // loss step: bucket table of the sparse screen targets
     unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
-    cudaStream_t lane_stream[4] = {};            // internal streams of the lanes of drt_ray_loss_step
-    cudaEvent_t lane_event[9] = {};              // fork, forward done x4, done x4
-    unsigned long long* last_ctl[4] = {};        // control blocks (one per lane) of the latest drt_ray_loss_step (drt_bvh_last_counts)
+    cudaStream_t lane_stream[8] = {};            // internal streams of the lanes of drt_ray_loss_step
+    cudaEvent_t lane_event[17] = {};             // fork, forward done x8, done x8
+    unsigned long long* last_ctl[8] = {};        // control blocks (one per lane) of the latest drt_ray_loss_step (drt_bvh_last_counts)
     int64_t last_tiles = 0;                      // its number of 32-ray tiles (0: no beam pass)
     int work_slot = 0;
     int build_blocks_per_sm = 0;                 // co-resident blocks of lbvh_build_kernel (0: no cooperative launch)
@@ -236,11 +239,18 @@ int beam_tiles_per_fetch(int64_t N, int warps)
     return tpb;
 }
 
-constexpr int kMaxLanes = 4;
+constexpr int kMaxLanes = 8;
 
-__global__ void sum_counts_kernel(const int* a, const int* b, const int* c, const int* d, int32_t* out)
+struct LaneCounts {
+    const int* p[kMaxLanes];
+};
+__global__ void sum_counts_kernel(LaneCounts c, int n, int32_t* out)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *out = *a + (b ? *b : 0) + (c ? *c : 0) + (d ? *d : 0);
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int s = 0;
+        for (int k = 0; k < n; ++k) s += *c.p[k];
+        *out = s;
+    }
 }
 
 // clamp + count out-of-range indices so that no later kernel can fault on a bad face list
@@ -446,8 +456,8 @@ int drt_bvh_create(int device, drt_bvh** out)
         if (coop) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->fused6_blocks_per_sm, wf_fused_kernel<6>, 128, 0));
     }
 
-    for (int k = 0; k < 4; ++k) CU(cudaStreamCreateWithFlags(&b->lane_stream[k], cudaStreamNonBlocking));
-    for (int k = 0; k < 9; ++k) CU(cudaEventCreateWithFlags(&b->lane_event[k], cudaEventDisableTiming));
+    for (int k = 0; k < kMaxLanes; ++k) CU(cudaStreamCreateWithFlags(&b->lane_stream[k], cudaStreamNonBlocking));
+    for (int k = 0; k < 1 + 2 * kMaxLanes; ++k) CU(cudaEventCreateWithFlags(&b->lane_event[k], cudaEventDisableTiming));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[0], ls_loss_bwd_kernel<false, false>, 128, 0));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[1], ls_loss_bwd_kernel<true, false>, 128, 0));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->bwd_blocks[2], ls_loss_bwd_kernel<true, true>, 128, 0));
@@ -533,11 +543,11 @@ int drt_bvh_last_counts(const drt_bvh* b, void* stream, int64_t out[6])
     for (int k = 0; k < 6; ++k) out[k] = 0;
     if (!b->last_ctl[0]) return DRT_OK;
     DeviceGuard g(b->device);
-    unsigned long long h[4][8] = {};
-    for (int k = 0; k < 4; ++k)
+    unsigned long long h[kMaxLanes][8] = {};
+    for (int k = 0; k < kMaxLanes; ++k)
         if (b->last_ctl[k]) CU(cudaMemcpyAsync(h[k], b->last_ctl[k], sizeof h[k], cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kMaxLanes; ++k) {
         const int* c = reinterpret_cast<const int*>(h[k]);
         out[0] += c[6]; out[1] += c[7]; out[2] += c[8];   // entry hits, survivors of both refractions, valid paths
         out[4] += b->last_tiles ? c[10] : 0;              // tiles kept by the beam pass
@@ -862,21 +872,28 @@ int drt_ray_loss_step_beams(drt_bvh* b, const double* V64, const double* origin,
     // measured on B200 (C4): 9 views (6.2 M rays) 1.32 -> 1.27 ms with two lanes, 72 views (49.8 M rays) 5.77 -> 5.85 ms: the
     // tails only matter when a stage lasts a few hundred microseconds, so large batches stay on one lane
     int n_lanes = 1;
-    int64_t cut[kMaxLanes + 1] = {0, N, N, N, N};  // lane k = rays [cut[k], cut[k+1])
-    if (tuning().lanes >= 2 && b->lane_stream[0] && N >= (1 << 17) && N > tuning().direct_max_rays && (N <= tuning().lanes_max_rays || tuning().lanes_forced)) {
+    int64_t cut[kMaxLanes + 1];  // lane k = rays [cut[k], cut[k+1])
+    cut[0] = 0;
+    for (int k = 1; k <= kMaxLanes; ++k) cut[k] = N;
+    // round 2, final kernels: above 16 M rays FOUR lanes win as well -- not for the tails (2 % of a stage there) but because the
+    // latency-bound loss/backward kernel of one lane (occupancy 25 %) overlaps the query kernels of the others: C4 72 views
+    // 5.62 -> 5.52 ms, C3 7.70 -> 7.47, C5 (32 views) 14.77 -> 14.55; 3 / 4 / 6 / 8 lanes at C4: 5.51 / 5.52 / 5.54 / 5.58
+    const int want_lanes = tuning().lanes_forced ? tuning().lanes : (N <= tuning().lanes_max_rays ? tuning().lanes : tuning().lanes_big);
+    if (want_lanes >= 2 && b->lane_stream[0] && N >= (1 << 17) && N > tuning().direct_max_rays) {
         // split at image boundaries when there are enough images, else at 32-ray batches (= pixel tiles: the item -> ray map
         // below is the one of the WHOLE batch, so a lane may start in the middle of an image)
-        const int64_t unit = (img > 0 && N % img == 0 && N / img >= tuning().lanes) ? img : 32;
+        const int64_t unit = (img > 0 && N % img == 0 && N / img >= want_lanes) ? img : 32;
         if (unit > 0) {
             const int64_t units = N / unit;
-            n_lanes = (int)std::min<int64_t>(tuning().lanes, std::max<int64_t>(1, units));
+            n_lanes = (int)std::min<int64_t>(want_lanes, std::max<int64_t>(1, units));
             for (int k = 1; k < n_lanes; ++k) cut[k] = (units * k / n_lanes) * unit;
             for (int k = n_lanes; k <= kMaxLanes; ++k) cut[k] = N;
             for (int k = 0; k < n_lanes; ++k)
                 if (cut[k + 1] <= cut[k]) { n_lanes = 1; cut[1] = N; break; }  // degenerate split: one lane
         }
     }
-    cudaStream_t ls[kMaxLanes] = {st, st, st, st};
+    cudaStream_t ls[kMaxLanes];
+    for (int k = 0; k < kMaxLanes; ++k) ls[k] = st;
     if (n_lanes > 1) {
         CU(cudaEventRecord(b->lane_event[0], st));  // fork: the lanes start after everything enqueued on the caller's stream
         for (int k = 0; k < n_lanes; ++k) {
@@ -1006,8 +1023,9 @@ int drt_ray_loss_step_beams(drt_bvh* b, const double* V64, const double* origin,
         CU(cudaStreamWaitEvent(st, b->lane_event[1 + kMaxLanes + k], 0));
     }
     if (n_paths) {
-        sum_counts_kernel<<<1, 32, 0, st>>>(lane[0].countS, n_lanes > 1 ? lane[1].countS : nullptr, n_lanes > 2 ? lane[2].countS : nullptr,
-                                            n_lanes > 3 ? lane[3].countS : nullptr, n_paths);
+        LaneCounts lc{};
+        for (int k = 0; k < n_lanes; ++k) lc.p[k] = lane[k].countS;
+        sum_counts_kernel<<<1, 32, 0, st>>>(lc, n_lanes, n_paths);
         ++g_launches;
     }
     return DRT_OK;
