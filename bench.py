@@ -1032,7 +1032,10 @@ def run_b200(args):
                        "bvh": "refit each step" if args.refit else "full LBVH rebuild each step", "loss_path": args.loss_path,
                        "launch": "one CUDA graph replay per step" if graph is not None else "stream launches",
                        "fwd_route": ("one thread per path (ls_direct_kernel): batch <= direct_max_rays" if args.loss_path == "step" and direct_route
-                                     else "staged wavefront (beam, Q1, R1, Q2, R2, Q3)"),
+                                     else "staged wavefront (beam, Q1, R1, Q2, R2, Q3)" + (
+                                         " in %d lanes (internal streams over parts of the batch; phases_ms.fwd ends when ALL lanes are past their forward part, "
+                                         "so it contains the other lanes' loss/backward work)" % stage_counts["lanes"]
+                                         if stage_counts and stage_counts.get("lanes", 0) > 1 else "")),
                        "l2": "inputs larger than L2 (%.1f GB of rays per step per GPU)" % (n_local * 48 / 1e9),
                        "tile_beams": ("per-tile direction intervals of the fixed view set prepared once at load time (drt_tile_beams, 1.5 B/ray resident)"
                                       if beams is not None else "derived from the rays inside every step"),

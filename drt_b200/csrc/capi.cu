@@ -171,6 +171,7 @@ struct drt_bvh {
     unsigned long long* work = nullptr;          // ring of work counters of the persistent tracer
     cudaStream_t lane_stream[8] = {};            // internal streams of the lanes of drt_ray_loss_step
     cudaEvent_t lane_event[17] = {};             // fork, forward done x8, done x8
+    int last_lanes = 0;                          // lanes of the latest drt_ray_loss_step (0: the one-thread-per-path route)
     unsigned long long* last_ctl[8] = {};        // control blocks (one per lane) of the latest drt_ray_loss_step (drt_bvh_last_counts)
     int64_t last_tiles = 0;                      // its number of 32-ray tiles (0: no beam pass)
     int work_slot = 0;
@@ -553,6 +554,7 @@ int drt_bvh_last_counts(const drt_bvh* b, void* stream, int64_t out[6])
         out[4] += b->last_tiles ? c[10] : 0;              // tiles kept by the beam pass
     }
     out[3] = b->last_tiles;
+    out[5] = b->last_lanes;
     return DRT_OK;
 }
 
@@ -943,6 +945,7 @@ int drt_ray_loss_step_beams(drt_bvh* b, const double* V64, const double* origin,
     const bool beam = DRT_QNODE && tuning().beam && (pol[0] & 0xff) == 32;
     // small batches: the whole forward path of a ray in one thread (ls_direct_kernel), then the usual loss/backward kernel
     const bool direct = n_lanes == 1 && N <= tuning().direct_max_rays;
+    b->last_lanes = direct ? 0 : n_lanes;
     if (direct) {
         Lane& l = lane[0];
         const int dg = (int)std::min<int64_t>(blocks_for(l.n, 128), (int64_t)b->sm_count * 16);

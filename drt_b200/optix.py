@@ -110,10 +110,10 @@ class optix_mesh:  # noqa: N801  (name fixed by the reference, optix_extend.cpp:
 
     def last_counts(self):
         """stage counters of the latest fused ray-loss step (synchronises): entry hits, alive after both refractions, valid
-        paths, tiles seen / kept by the beam pass"""
+        paths, tiles seen / kept by the beam pass, lanes the call ran on (0: one-thread-per-path route)"""
         a = (C.c_int64 * 6)()
         _lib.call("drt_bvh_last_counts", self._h, _stream_ptr(self.device), a)
-        return dict(zip(("entry_hits", "alive", "valid_paths", "tiles", "tiles_kept"), list(a)))
+        return dict(zip(("entry_hits", "alive", "valid_paths", "tiles", "tiles_kept", "lanes"), list(a)))
 
     def bad_indices(self):
         out = C.c_int(0)

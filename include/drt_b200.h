@@ -89,7 +89,7 @@ DRT_API int drt_bvh_info(const drt_bvh* bvh, int64_t info[8]);
 /* Stage counters of the latest drt_ray_loss_step on this handle (synchronises `stream`; diagnostics for bench.py, no
  * reference counterpart -- the reference's equivalents are the lengths of the Ray sets after each Ray.select,
  * DiffRender.py:538-544): out = {entry hits, rays alive after both refractions, valid paths, 32-ray tiles seen by the
- * beam pass, tiles it kept, 0}. */
+ * beam pass, tiles it kept, lanes (internal streams) the call ran on -- 0 for the one-thread-per-path route}. */
 DRT_API int drt_bvh_last_counts(const drt_bvh* bvh, void* stream, int64_t out[6]);
 
 /*

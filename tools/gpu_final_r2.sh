@@ -13,12 +13,16 @@ timeout 300 $B --config C3 > gpurun_out/r02_bench_c3_n1.json 2> gpurun_out/r02_b
 timeout 300 $B --config C2 > gpurun_out/r02_bench_c2_n1.json 2> gpurun_out/r02_bench_c2.err
 timeout 300 $B --config C5 --views 32 > gpurun_out/r02_bench_c5_32views_n1.json 2> gpurun_out/r02_bench_c5.err
 timeout 300 $B --views 9 > gpurun_out/r02_bench_c4_9views_n1.json 2> /dev/null
+timeout 300 $B --views 1 > gpurun_out/r02_bench_c4_1view_n1.json 2> /dev/null
+timeout 300 $B --config C3 --views 1 > gpurun_out/r02_bench_c3_1view_n1.json 2> /dev/null
 timeout 300 $B --refit > gpurun_out/r02_bench_c4_refit.json 2> /dev/null
 DRT_BEAM=0 timeout 300 $B > gpurun_out/r02_bench_c4_nobeam.json 2> /dev/null
+DRT_LANES_BIG=1 timeout 300 $B > gpurun_out/r02_bench_c4_one_lane.json 2> /dev/null
 P="$B --no-parity-check --graph off"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/r02_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 600 --csv --log-file gpurun_out/r02_launches.csv \
     $P --steps 2 --warmup 3 > gpurun_out/r02_ncu_launch.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"ls_|sort_|fit_|emit_" -o gpurun_out/r02_prof_step -f \
+# the --set full capture runs the step on ONE lane (DRT_LANES_BIG=1): the same kernels, one instance of each instead of four
+DRT_LANES_BIG=1 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"ls_|sort_|fit_|emit_" -o gpurun_out/r02_prof_step -f \
     $P --steps 1 --warmup 3 > gpurun_out/r02_ncu_full.log 2>&1
 ls -la gpurun_out/r02_prof_step.ncu-rep
 python - <<'PY'
