@@ -33,7 +33,7 @@ def test_header_cites_reference_for_each_entry_point():
     src = open(os.path.join(ROOT, "include", "drt_b200.h")).read()
     for fn in ("drt_bvh_create", "drt_bvh_build", "drt_bvh_update_vert", "drt_bvh_set_image_size", "drt_closest_hit", "drt_trace_fwd",
                "drt_trace_bwd", "drt_ray_loss_grad", "drt_ray_loss_step", "drt_ray_loss_step_beams", "drt_tile_beams", "drt_generate_rays",
-               "drt_comm_create"):
+               "drt_comm_create", "drt_trace_fwd_smooth", "drt_trace_bwd_smooth", "drt_plane_hit", "drt_plane_hit_bwd", "drt_tuning_set"):
         i = src.index(f" {fn}(")
         assert re.search(r"(optix_extend\.cpp|DiffRender\.py|optim\.py|captured_data\.py):\d+", src[max(0, i - 3500):i]), fn
 

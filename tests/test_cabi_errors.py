@@ -34,6 +34,19 @@ def test_null_and_range_arguments_cpu():
     assert "null handle" in _err()
     assert lib.drt_generate_rays(4, 4, None, None, None, None, None) == 1 and "null buffer" in _err()
     assert lib.drt_kernel_launches() >= 0
+    # the optional modes and the tuning switch (pure host-side argument checks)
+    assert lib.drt_trace_fwd_smooth(None, None, None, None, None, 0, 1.0, 1.5, None, None, None, None, None, None) == 1
+    assert lib.drt_trace_bwd_smooth(None, None, None, None, None, 0, 1.0, 1.5, None, None, None, None, None, None, None) == 1
+    assert lib.drt_plane_hit(None, None, None, -1, None, None, None, None) == 1 and "N < 0" in _err()
+    assert lib.drt_plane_hit(None, None, None, 0, None, None, None, None) == 0
+    assert lib.drt_plane_hit_bwd(None, None, None, 3, None, None, None, None, None) == 1 and "null buffer" in _err()
+    old = lib.drt_tuning_get(b"direct_max_rays")
+    assert old >= 0
+    assert lib.drt_tuning_set(b"direct_max_rays", 12345) == 0 and lib.drt_tuning_get(b"direct_max_rays") == 12345
+    assert lib.drt_tuning_set(b"direct_max_rays", -1) == 1 and lib.drt_tuning_get(b"direct_max_rays") == 12345
+    assert lib.drt_tuning_set(b"no_such_switch", 1) == 1 and "unknown key" in _err()
+    assert lib.drt_tuning_set(None, 1) == 1 and lib.drt_tuning_get(b"no_such_switch") == -1
+    assert lib.drt_tuning_set(b"direct_max_rays", old) == 0
 
 
 @pytest.mark.gpu
