@@ -88,7 +88,9 @@ struct Tuning {
         const char* t = getenv("DRT_FWD_THRESH");
         if (t && atoi(t) >= 1 && atoi(t) <= 32) thresh = atoi(t);
         const char* vt = getenv("DRT_VOTE");
-        const int vote = (vt && atoi(vt) >= 0 && atoi(vt) <= 31) ? atoi(vt) : 4;  // measured at C4: 0: 6.68, 4: 6.37, 8: 6.43, 12: 6.56 ms forward
+        // round 1 (one vote per node step): 0: 6.68, 4: 6.37, 8: 6.43, 12: 6.56 ms forward at C4; with one vote per 8 steps (trace.cuh:
+        // DRT_VOTE_EVERY) the best threshold is 1 -- leave the walk as soon as any lane is blocked when the vote comes
+        const int vote = (vt && atoi(vt) >= 0 && atoi(vt) <= 31) ? atoi(vt) : 1;
         for (int q = 0; q < 3; ++q) {
             char name[32];
             int th = thresh, vo = vote;

@@ -631,8 +631,12 @@ __device__ __forceinline__ void walk(const BvhView& B, const RayQ& q, float tmax
 // tests while the others still have a short queue; with the per-lane loop a lane that has filled its queue idles until the
 // SLOWEST lane of the warp has filled its own.  All 32 lanes must call this.
 // Votes cost ~12 of the ~70 instructions of an iteration: measured at C4, one vote per 1 / 2 / 3 / 4 steps: 5.56 / 5.29 / 5.19 / 5.21 ms forward.
+// Re-measured on the final kernels of round 2 (beam culling, prepared tile beams, four lanes; C4 step in ms), steps per vote x vote
+// threshold: 3x4 5.53 | 4x4 5.48 | 6x2 5.36 | 6x1 5.32 | 8x3 5.37 | 8x2 5.32 | 8x1 5.27 | 9x1 5.25 | 10x1 5.27 | 12x1 5.35 | 16x2 5.49
+// -- the warp walks in bursts of 8 node steps and leaves the loop as soon as ONE lane is blocked at a vote; C3 7.48 -> 7.12,
+// 9 views 1.054 -> 1.005, C5 (32 views) 14.54 -> 13.99.
 #ifndef DRT_VOTE_EVERY
-#define DRT_VOTE_EVERY 3
+#define DRT_VOTE_EVERY 8
 #endif
 constexpr int kVoteEvery = DRT_VOTE_EVERY;
 #ifndef DRT_VOTE_EVERY4
