@@ -1,4 +1,4 @@
 #!/bin/bash
-# vote every 8 steps, threshold 1: queue depth, full-queue walk, neighbours
+# the remaining runtime knobs re-checked after the vote re-tune (C4 72 views)
 mkdir -p gpurun_out
-BENCH_ARGS="--no-parity-check" STEPS=15 DRT_VOTE=1 bash tools/gpu_sweep.sh r2ck6 "ve8|DRT_VOTE=1|ve8" "ve8d2|DRT_VOTE=1|ve8d2" "ve8d4|DRT_VOTE=1|ve8d4" "ve8fq0|DRT_VOTE=1|ve8fq0" "ve7|DRT_VOTE=1|ve7" "ve9|DRT_VOTE=1|ve9" "ve8d4_v2|DRT_VOTE=2|ve8d4"
+BENCH_ARGS="--no-parity-check" STEPS=15 bash tools/gpu_sweep.sh r2ck7 "default||-" "q2t28|DRT_THRESH_Q2=28|-" "q2t24|DRT_THRESH_Q2=24|-" "q3t24|DRT_THRESH_Q3=24|-" "q23t16|DRT_THRESH_Q2=16 DRT_THRESH_Q3=16|-" "tile8x4|DRT_TILE_SHAPE=8x4|-" "lanes3|DRT_LANES=3|-" "lanes6|DRT_LANES=6|-" "vote0|DRT_VOTE=0|-"
