@@ -506,7 +506,22 @@ def run_b200(args):
     # every view by its rank's measured / estimated time, reassigns (LPT, identical on every rank) and regenerates the inputs.
     rebalance_log = []
     if world > 1 and args.shard == "balanced" and args.loss_path == "step" and args.rebalance > 0:
-        for _round in range(args.rebalance):
+        def use_views(new_mine):
+            """switches this rank to another set of views: inputs, prepared beams, two untimed steps"""
+            nonlocal mine, cams, n_local, origin, ray_dir, screen, valid, origins, sparse, beams
+            mine = new_mine
+            cams = [cfg["cams"][k] for k in mine]
+            n_local = len(cams) * n_pix
+            del origin, ray_dir, screen, valid, origins, sparse
+            torch.cuda.empty_cache()
+            origin, ray_dir, screen, valid, origins, sparse = make_inputs(cams)
+            beams = make_beams()
+            for _ in range(2):
+                loss_buf.zero_()
+                step(origin, ray_dir, screen, valid, g_dir)
+
+        tried = []  # (max rank time, the assignment of every rank) of every assignment that was measured
+        for _round in range(args.rebalance + 1):
             torch.cuda.synchronize(dev)
             dist.barrier()
             r0, r1 = ev(), ev()
@@ -520,27 +535,28 @@ def run_b200(args):
             dist.all_gather(g_all, torch.tensor([r0.elapsed_time(r1) / 5], dtype=torch.float64, device=dev))
             times = [float(x.item()) for x in g_all]
             assign = [ddist.shard_views_balanced(costs, r, world) for r in range(world)]
+            assert assign[rank] == mine
+            tried.append((max(times), assign))
+            rebalance_log.append({"rank_ms": times, "max_over_mean": max(times) / (sum(times) / world)})
+            if _round == args.rebalance:
+                break
             est = [sum(costs[k] for k in a) for a in assign]
             norm = sum(est) / sum(times)
             for r, a in enumerate(assign):
                 for k in a:
                     costs[k] *= times[r] * norm / est[r]
-            rebalance_log.append({"rank_ms": times, "max_over_mean": max(times) / (sum(times) / world)})
             new_mine = ddist.shard_views_balanced(costs, rank, world)
             changed = torch.tensor([int(new_mine != mine)], device=dev)
             dist.all_reduce(changed, op=dist.ReduceOp.MAX)
             if not changed.item():
                 break
-            mine = new_mine
-            cams = [cfg["cams"][k] for k in mine]
-            n_local = len(cams) * n_pix
-            del origin, ray_dir, screen, valid, origins, sparse
-            torch.cuda.empty_cache()
-            origin, ray_dir, screen, valid, origins, sparse = make_inputs(cams)
-            beams = make_beams()
-            for _ in range(2):
-                loss_buf.zero_()
-                step(origin, ray_dir, screen, valid, g_dir)
+            use_views(new_mine)
+        # the refinement is not monotonic (a rank's time is not only its views' cost): keep the best assignment that was MEASURED
+        # (every rank holds the same gathered times, so every rank picks the same one)
+        best = min(range(len(tried)), key=lambda i: (tried[i][0], i))
+        rebalance_log.append({"kept": best, "of": len(tried)})
+        if tried[best][1][rank] != mine:  # no collective inside: a rank whose views are the same in both assignments skips it
+            use_views(tried[best][1][rank])
         sync_all()
     # The ~30 launches of a step (LBVH rebuild, 8 kernels of the fused ray-loss step, the autograd scale) captured ONCE as a CUDA
     # graph and replayed: same kernels, same arguments (the library's scratch and torch's graph pool are static), no Python or
